@@ -1,0 +1,200 @@
+/*
+ * petgem_b200 -- C ABI of the B200-native PETGEM hot path.
+ *
+ * The reference (PETGEM v1.0, pure Python) has no FFI; its hot path is reached
+ * through Python calls (kernel.py:64-73 -> petgem/solver.py -> petgem/hvfem.py and
+ * petsc4py).  Each entry point below replaces one of those call sites with a
+ * batched device kernel; the comment on each cites the reference interface it
+ * stands in for (paths relative to /root/reference).  INTEGRATION.md shows the
+ * ctypes binding a PETGEM maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array pointer is a DEVICE pointer owned
+ *    by the caller unless the name ends in _host; the library never frees caller
+ *    memory and keeps no global state besides the last error string (thread local);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *    asynchronous on that stream unless stated otherwise;
+ *  - every function returns 0 on success or a negative code (PG_E*); it never calls
+ *    exit().  The Python layer maps a failure to the reference convention
+ *    Print.master(msg); exit(-1) (e.g. hvfem.py:284-286);
+ *  - complex numbers are interleaved (re, im) doubles, i.e. numpy complex128 /
+ *    PetscScalar in a --with-scalar-type=complex build;
+ *  - indices are int32 (dof/entity ids) and int64 (row pointers / nnz offsets).
+ *
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef PETGEM_B200_H
+#define PETGEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_EINVAL -22   /* bad argument (order outside 1..6, null pointer, ...) */
+#define PG_ENOMEM -12   /* device allocation failed */
+#define PG_ECUDA -5     /* CUDA runtime error; see pg_last_error() */
+#define PG_ERANGE -34   /* a size exceeds what the index types can hold */
+
+#define PG_MAX_ORDER 6
+#define PG_SLOTS 11     /* entity slots of a tetrahedron: 6 edges, 4 faces, 1 interior */
+
+int pg_version(void);
+const char *pg_last_error(void);
+
+/* number of dofs per element / edge / face / interior for order p (hvfem.py:44-48) */
+int pg_ndof_element(int p);
+int pg_ndof_edge(int p);
+int pg_ndof_face(int p);
+int pg_ndof_volume(int p);
+/* size of the orientation-expanded function set: 6p + 24p(p-1) + p(p-1)(p-2)/2 */
+int pg_nexp(int p);
+
+/* ---------------------------------------------------------------------------
+ * a2 + a3: computeJacobian (hvfem.py:101-119) and computeElementOrientation
+ * (hvfem.py:122-220), batched over elements; inputs are the rows of the scratch
+ * files read at solver.py:193-211.
+ *   nodes      [T,12] f64  xyz of the 4 vertices          (nodes.dat)
+ *   elemsN     [T,4]  i32  global node ids                (meshConnectivity.dat)
+ *   elemsE     [T,6]  i32  global edge ids                (edges.dat)
+ *   edgesNodes [T,12] i32  (min,max) node pair per edge   (edgesNodes.dat)
+ *   facesEdges [T,12] i32  3 global edges per local face  (facesEdges.dat)
+ *   sigma      [T,2]  f64  (sigma_h, sigma_v)             (conductivityModel.dat)
+ * outputs
+ *   geo  [T,12] f64  gK[6] = sym(J J^T / detJ), gM[6] = sym(detJ J^-T diag(sh,sh,sv) J^-1)
+ *                    packed (00,11,22,01,02,12); detJ is SIGNED (hvfem.py:265)
+ *   code [T]    u32  bits 0..5 edge orientation, bits 6+3f..8+3f face code 0..5
+ * --------------------------------------------------------------------------- */
+int pg_element_geometry(int64_t T, const double *nodes, const int32_t *elemsN, const int32_t *elemsE,
+                        const int32_t *edgesNodes, const int32_t *facesEdges, const double *sigma,
+                        double *geo, uint32_t *code, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * a4 (+a5, a6): computeElementalMatrices (hvfem.py:223-316), batched.
+ *   table [nexp,nexp,12] f64: per expanded pair (J,K) SK[6] then SM[6]
+ *         (petgem_b200/basis.py:element_tables; built once per order)
+ *   Me, Ke [T,n,n] f64 row-major (either may be NULL)
+ * --------------------------------------------------------------------------- */
+int pg_element_matrices(int64_t T, int p, const double *geo, const uint32_t *code, const double *table,
+                        double *Me, double *Ke, void *stream);
+
+/* solver.py:223-224: Ae = K - i*omega*mu*M, flattened row-major; mass_scale = -omega*mu.
+ *   Ae [T,n,n] complex128 */
+int pg_element_systems(int64_t T, int p, const double *geo, const uint32_t *code, const double *table,
+                       double mass_scale, double *Ae, void *stream);
+
+/* a7: computeConnectivityDOFS (hvfem.py:15-98): dofs [T,n] i32 */
+int pg_connectivity_dofs(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
+                         int64_t nFaces, int32_t *dofs, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * a8 + a9 (symbolic half): what createParallelMatrix + MatSetValues/MatAssembly
+ * (parallel.py:150-177, solver.py:188-235) decide about the sparsity pattern:
+ * union of element dof cliques, explicit zeros kept, columns ascending.
+ *
+ * The plan is an opaque host object that owns the device arrays of the symbolic
+ * phase (entity incidence lists, per-entity column lists, slot positions).
+ *   ent_order_host: NULL = reference numbering (edge dofs, face dofs, interior
+ *       dofs; hvfem.py:50-71), else a permutation of the nEnt global entity ids
+ *       (edges 0..nE-1, faces nE.., interiors nE+nF..) giving the internal row
+ *       order; pg_plan_locality_order() builds the element-major one.
+ *   row_begin,row_end: rows (in the numbering in use) owned by this process,
+ *       PETSc-style contiguous block; pass 0, -1 for all rows.  Must fall on
+ *       entity boundaries (pg_plan_entity_aligned_split helps).
+ * Synchronous (host decisions depend on device counts).
+ * --------------------------------------------------------------------------- */
+typedef struct pg_plan pg_plan;
+
+int pg_plan_create(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
+                   int64_t nFaces, const int32_t *ent_order_host, int64_t row_begin, int64_t row_end,
+                   pg_plan **plan, void *stream);
+void pg_plan_destroy(pg_plan *plan);
+
+/* element-major entity order (entities sorted by first incident element, then slot) */
+int pg_plan_locality_order(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
+                           int64_t nFaces, int32_t *ent_order_host, void *stream);
+
+int64_t pg_plan_num_dofs(const pg_plan *plan);      /* N (global) */
+int64_t pg_plan_num_entities(const pg_plan *plan);  /* entities that carry dofs */
+int64_t pg_plan_local_rows(const pg_plan *plan);    /* row_end - row_begin */
+int64_t pg_plan_row_begin(const pg_plan *plan);
+int64_t pg_plan_nnz(const pg_plan *plan);           /* nnz of the owned rows */
+int64_t pg_plan_contributions(const pg_plan *plan); /* sum over owned rows of element contributions */
+int pg_plan_max_row_length(const pg_plan *plan);
+
+/* CSR of the owned rows: rowptr [local_rows+1] i64 (starting at 0), colidx [nnz] i32 (global cols) */
+int pg_plan_csr(const pg_plan *plan, int64_t *rowptr, int32_t *colidx, void *stream);
+/* perm [N] i32: row/col index (numbering in use) of every reference dof id */
+int pg_plan_dof_permutation(const pg_plan *plan, int32_t *perm, void *stream);
+/* smallest entity-aligned row >= row (numbering in use); host, synchronous */
+int64_t pg_plan_entity_aligned_row(const pg_plan *plan, int64_t row);
+
+/* ---------------------------------------------------------------------------
+ * a10 (fused form): tell the plan which entities are Dirichlet so that
+ * pg_assemble can apply MatZeroRowsColumns (solver.py:562) while it assembles.
+ * In PETGEM the boundary dofs are always ALL dofs of boundary edges and boundary
+ * faces (mesh.py:280-321), so the set is given per entity:
+ *   bd_entity [nEnt] u8 (global entity ids: edges, then faces, then interiors);
+ *   NULL clears it.  elemsE/elemsF as given to pg_plan_create.
+ * --------------------------------------------------------------------------- */
+int pg_plan_set_dirichlet(pg_plan *plan, const int32_t *elemsE, const int32_t *elemsF, const uint8_t *bd_entity,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------
+ * a1 + a4 + a9 (numeric half): the element loop solver.py:191-230 fused with the
+ * scatter-add: every owned row gathers its element contributions in ascending
+ * element order (the order MatSetValues(ADD_VALUES) is called in), no atomics,
+ * bit-reproducible.  vals [nnz] complex128 in pg_plan_csr order.
+ *   apply_dirichlet != 0: rows/columns of the entities given to
+ *       pg_plan_set_dirichlet are zeroed and `diag` put on their diagonal, i.e.
+ *       the result equals assembly followed by A.zeroRowsColumns(bd, diag).
+ * --------------------------------------------------------------------------- */
+int pg_assemble(const pg_plan *plan, const double *geo, const uint32_t *code, const double *table,
+                double mass_scale, int apply_dirichlet, double diag, double *vals, void *stream);
+
+/* a10: A.zeroRowsColumns(bd) (solver.py:562; petsc4py default diag = 1.0) on an
+ * assembled CSR block; bd_mask [N] u8 over global columns; row_begin = first owned row. */
+int pg_zero_rows_columns(int64_t local_rows, int64_t row_begin, const int64_t *rowptr, const int32_t *colidx,
+                         const uint8_t *bd_mask, double diag, double *vals, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * a11: the arithmetic inside KSP.solve (solver.py:584-590): MatMult and the
+ * Vec kernels GMRES/BiCGStab call.  x is the FULL (gathered) vector, y the owned
+ * block.  Scalars live in device memory so a Krylov cycle needs no host sync.
+ * --------------------------------------------------------------------------- */
+int pg_spmv(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+            const double *x, double *y, void *stream);
+/* diag [local_rows] complex128 of the owned block (for PCJACOBI) */
+int pg_csr_diagonal(int64_t local_rows, int64_t row_begin, const int64_t *rowptr, const int32_t *colidx,
+                    const double *vals, double *diag, void *stream);
+
+/* y += alpha x ; alpha read from device memory (complex) */
+int pg_zaxpy(int64_t n, const double *alpha, const double *x, double *y, void *stream);
+/* y = x + beta y */
+int pg_zaypx(int64_t n, const double *beta, const double *x, double *y, void *stream);
+/* w = a x + b y + c z (any coefficient pointer NULL = term skipped); w may alias x,y,z */
+int pg_zaxpbypcz(int64_t n, const double *a, const double *x, const double *b, const double *y, const double *c,
+                 const double *z, double *w, void *stream);
+/* x *= alpha, alpha complex on device; if inv_real != 0: x *= 1/Re(alpha) (normalisation) */
+int pg_zscal(int64_t n, const double *alpha, int inv_real, double *x, void *stream);
+/* z = x .* y (PCJACOBI apply with y = 1/diag) */
+int pg_zpointwise_mult(int64_t n, const double *x, const double *y, double *z, void *stream);
+/* out[0] = sum conj(x_i) y_i  (VecDot(y,x) convention: PETSc conjugates the 2nd arg);
+ * deterministic two-stage tree, work = pg_reduce_workspace_bytes() */
+int pg_zdotc(int64_t n, const double *x, const double *y, double *out, void *work, void *stream);
+/* VecMDot: out[i] = sum conj(V_i) . w for k vectors V_i = V + i*ldv (complex elements), one pass over w */
+int pg_zmdotc(int64_t n, int k, const double *V, int64_t ldv, const double *w, double *out, void *work,
+              void *stream);
+/* VecMAXPY: w += sum_i scale*alpha[i] V_i (alpha complex on device), one pass over w */
+int pg_zmaxpy(int64_t n, int k, const double *alpha, double scale, const double *V, int64_t ldv, double *w,
+              void *stream);
+/* out[0] = sum |x_i|^2 (real, stored as complex with zero imaginary part) */
+int pg_dznrm2sq(int64_t n, const double *x, double *out, void *work, void *stream);
+int64_t pg_reduce_workspace_bytes(int kmax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETGEM_B200_H */

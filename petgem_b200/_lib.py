@@ -1,0 +1,143 @@
+"""ctypes binding of libpetgem_b200.so (the C ABI declared in include/petgem_b200.h).
+
+The library is built in-tree by :func:`build` (nvcc, sm_100a only).  There is no
+fallback: if the shared object is missing or a CUDA device is absent, the product
+path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu"]
+HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class PetgemB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into petgem_b200/libpetgem_b200.so."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_i64, _i32, _p, _d = C.c_int64, C.c_int, C.c_void_p, C.c_double
+
+# name -> (restype, argtypes); must list every symbol include/petgem_b200.h declares
+SIGNATURES = {
+    "pg_version": (C.c_int, []),
+    "pg_last_error": (C.c_char_p, []),
+    "pg_ndof_element": (C.c_int, [_i32]),
+    "pg_ndof_edge": (C.c_int, [_i32]),
+    "pg_ndof_face": (C.c_int, [_i32]),
+    "pg_ndof_volume": (C.c_int, [_i32]),
+    "pg_nexp": (C.c_int, [_i32]),
+    "pg_element_geometry": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pg_element_matrices": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "pg_element_systems": (C.c_int, [_i64, _i32, _p, _p, _p, _d, _p, _p]),
+    "pg_connectivity_dofs": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _p]),
+    "pg_plan_create": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _i64, _i64, C.POINTER(_p), _p]),
+    "pg_plan_destroy": (None, [_p]),
+    "pg_plan_locality_order": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _p]),
+    "pg_plan_num_dofs": (_i64, [_p]),
+    "pg_plan_num_entities": (_i64, [_p]),
+    "pg_plan_local_rows": (_i64, [_p]),
+    "pg_plan_row_begin": (_i64, [_p]),
+    "pg_plan_nnz": (_i64, [_p]),
+    "pg_plan_contributions": (_i64, [_p]),
+    "pg_plan_max_row_length": (C.c_int, [_p]),
+    "pg_plan_csr": (C.c_int, [_p, _p, _p, _p]),
+    "pg_plan_dof_permutation": (C.c_int, [_p, _p, _p]),
+    "pg_plan_entity_aligned_row": (_i64, [_p, _i64]),
+    "pg_plan_set_dirichlet": (C.c_int, [_p, _p, _p, _p, _p]),
+    "pg_assemble": (C.c_int, [_p, _p, _p, _p, _d, _i32, _d, _p, _p]),
+    "pg_zero_rows_columns": (C.c_int, [_i64, _i64, _p, _p, _p, _d, _p, _p]),
+    "pg_spmv": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
+    "pg_csr_diagonal": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p]),
+    "pg_zaxpy": (C.c_int, [_i64, _p, _p, _p, _p]),
+    "pg_zaypx": (C.c_int, [_i64, _p, _p, _p, _p]),
+    "pg_zaxpbypcz": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pg_zscal": (C.c_int, [_i64, _p, _i32, _p, _p]),
+    "pg_zpointwise_mult": (C.c_int, [_i64, _p, _p, _p, _p]),
+    "pg_zdotc": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
+    "pg_zmdotc": (C.c_int, [_i64, _i32, _p, _i64, _p, _p, _p, _p]),
+    "pg_zmaxpy": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p]),
+    "pg_dznrm2sq": (C.c_int, [_i64, _p, _p, _p, _p]),
+    "pg_reduce_workspace_bytes": (_i64, [_i32]),
+}
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (raises if it has not been built)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PetgemB200Error(
+                "libpetgem_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pg_last_error().decode(errors="replace")
+        raise PetgemB200Error("%s failed with status %d: %s" % (what or "petgem_b200 call", rc, msg))
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def stream_ptr():
+    """The current torch CUDA stream as a cudaStream_t."""
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise PetgemB200Error("petgem_b200 needs a CUDA device (B200); there is no CPU fallback")

@@ -1,0 +1,44 @@
+// Symbolic assembly plan (device-resident), shared by pg_plan.cu and pg_assemble.cu.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+// One record per (entity, incident element): everything the numeric phase needs
+// to place a local element row into the entity's CSR rows.  32 bytes.
+struct __align__(16) IncRecord {
+    int32_t elem;                // element index t
+    uint16_t slotpos[PG_SLOTS];  // first position, in the entity's column list, of the dofs of slot s'
+    uint8_t slot;                // which slot of t this entity is
+    uint8_t pad0;
+    uint16_t bdmask;             // bit s' set: slot s' of t is a Dirichlet entity
+    uint16_t pad1;
+};
+static_assert(sizeof(IncRecord) == 32, "IncRecord must be 32 bytes");
+
+}  // namespace pg
+
+struct pg_plan {
+    int64_t T = 0;
+    int p = 0, n = 0, nslots = 0;
+    int64_t nE = 0, nF = 0, nEnt = 0, N = 0;
+    int64_t nInc = 0;
+    // entity order: block b <-> entity ent_order[b]
+    int32_t *ent_order = nullptr;   // [nEnt]
+    int32_t *blk_of_ent = nullptr;  // [nEnt]
+    int64_t *row_base = nullptr;    // [nEnt+1] first row (numbering in use) of block b
+    // incidence lists by entity id
+    int32_t *inc_ptr = nullptr;     // [nEnt+1]
+    pg::IncRecord *rec = nullptr;   // [nInc]
+    // column-entity lists by entity id
+    int64_t *colent_ptr = nullptr;  // [nEnt+1]
+    int32_t *colent = nullptr;      // [ncolent] global entity ids, ascending block position
+    int32_t *rowlen = nullptr;      // [nEnt] L(g) = row length of every row of entity g
+    int32_t *selfpos = nullptr;     // [nEnt] position of the entity's own dofs in its column list
+    // owned block range and value offsets
+    int64_t b0 = 0, b1 = 0, row_begin = 0, row_end = 0;
+    int64_t *valoff = nullptr;      // [b1-b0+1] offset into vals of the first row of owned block
+    int64_t nnz = 0, contributions = 0;
+    int max_rowlen = 0;
+    uint8_t *bd_entity = nullptr;   // [nEnt] own copy, set by pg_plan_set_dirichlet
+};

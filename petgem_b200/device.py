@@ -1,0 +1,287 @@
+"""Device-side objects of the hot path: element data, assembly plan, CSR matrix.
+
+torch is used for device memory, streams and (multi-GPU) torch.distributed only;
+every computation goes through the C ABI in include/petgem_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+
+import numpy as np
+import torch
+
+from . import basis
+from ._lib import PetgemB200Error, check, lib, ptr, require_cuda, stream_ptr
+
+MU0 = 4.0 * np.pi * 1e-7  # solver.py:175
+
+
+def _dev(device=None):
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+@functools.lru_cache(maxsize=None)
+def _table_host(p: int) -> np.ndarray:
+    SM, SK = basis.element_tables(p)
+    # [nexp, nexp, 12]: SK[0..5] then SM[0..5] for each expanded pair (J, K)
+    tab = np.concatenate([np.moveaxis(SK, 0, -1), np.moveaxis(SM, 0, -1)], axis=-1)
+    return np.ascontiguousarray(tab)
+
+
+_TABLE_CACHE = {}
+
+
+def element_table(p: int, device=None) -> torch.Tensor:
+    """Reference-element contraction table of order p on the device (built once)."""
+    dev = _dev(device)
+    key = (p, str(dev))
+    if key not in _TABLE_CACHE:
+        _TABLE_CACHE[key] = torch.from_numpy(_table_host(p)).to(dev)
+    return _TABLE_CACHE[key]
+
+
+class ElementData:
+    """Per-element inputs of the element loop (rows of the scratch files read at
+    solver.py:193-211), resident in HBM as flat SoA-of-rows arrays."""
+
+    def __init__(self, nodes, elemsN, elemsE, edgesNodes, facesEdges, elemsF, sigma, nEdges, nFaces, device=None):
+        dev = _dev(device)
+        T = int(np.asarray(elemsN).shape[0])
+
+        def f64(a, cols):
+            t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(T, cols))
+            return t.to(dev, non_blocking=False)
+
+        def i32(a, cols):
+            t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32).reshape(T, cols))
+            return t.to(dev, non_blocking=False)
+
+        self.T = T
+        self.nodes = f64(nodes, 12)
+        self.elemsN = i32(elemsN, 4)
+        self.elemsE = i32(elemsE, 6)
+        self.edgesNodes = i32(edgesNodes, 12)
+        self.facesEdges = i32(facesEdges, 12)
+        self.elemsF = i32(elemsF, 4)
+        self.sigma = f64(sigma, 2)
+        self.nEdges, self.nFaces = int(nEdges), int(nFaces)
+        self.device = dev
+
+    @classmethod
+    def from_mesh(cls, nodes_xyz, elemsN, elemsE, edgesNodes, elemsF, facesE, sigma, device=None):
+        """Build the per-element rows from global mesh tables (preprocessing.py:92-216)."""
+        elemsN = np.asarray(elemsN)
+        return cls(
+            np.asarray(nodes_xyz)[elemsN].reshape(elemsN.shape[0], 12),
+            elemsN,
+            elemsE,
+            np.asarray(edgesNodes)[np.asarray(elemsE)].reshape(elemsN.shape[0], 12),
+            np.asarray(facesE)[np.asarray(elemsF)].reshape(elemsN.shape[0], 12),
+            elemsF,
+            sigma,
+            np.asarray(edgesNodes).shape[0],
+            np.asarray(facesE).shape[0],
+            device=device,
+        )
+
+    def geometry(self):
+        """computeJacobian + computeElementOrientation for every element -> (geo [T,12], code [T])."""
+        geo = torch.empty((self.T, 12), dtype=torch.float64, device=self.device)
+        code = torch.empty((self.T,), dtype=torch.int32, device=self.device)
+        check(
+            lib().pg_element_geometry(
+                self.T, ptr(self.nodes), ptr(self.elemsN), ptr(self.elemsE), ptr(self.edgesNodes),
+                ptr(self.facesEdges), ptr(self.sigma), ptr(geo), ptr(code), stream_ptr(),
+            ),
+            "pg_element_geometry",
+        )
+        return geo, code
+
+    def dofs(self, p: int) -> torch.Tensor:
+        """computeConnectivityDOFS (hvfem.py:15-98) -> [T, n] int32."""
+        n = basis.ndof_element(p)
+        out = torch.empty((self.T, n), dtype=torch.int32, device=self.device)
+        check(
+            lib().pg_connectivity_dofs(self.T, p, ptr(self.elemsE), ptr(self.elemsF), self.nEdges, self.nFaces,
+                                       ptr(out), stream_ptr()),
+            "pg_connectivity_dofs",
+        )
+        return out
+
+
+def element_matrices(p: int, geo: torch.Tensor, code: torch.Tensor):
+    """Batched computeElementalMatrices (hvfem.py:223-316) -> (Me, Ke) [T,n,n] float64."""
+    T, n = geo.shape[0], basis.ndof_element(p)
+    Me = torch.empty((T, n, n), dtype=torch.float64, device=geo.device)
+    Ke = torch.empty_like(Me)
+    check(
+        lib().pg_element_matrices(T, p, ptr(geo), ptr(code), ptr(element_table(p, geo.device)), ptr(Me), ptr(Ke),
+                                  stream_ptr()),
+        "pg_element_matrices",
+    )
+    return Me, Ke
+
+
+def element_systems(p: int, geo: torch.Tensor, code: torch.Tensor, omega: float, mu: float = MU0):
+    """Batched Ae = K - i*omega*mu*M (solver.py:223) -> [T,n,n] complex128."""
+    T, n = geo.shape[0], basis.ndof_element(p)
+    Ae = torch.empty((T, n, n), dtype=torch.complex128, device=geo.device)
+    check(
+        lib().pg_element_systems(T, p, ptr(geo), ptr(code), ptr(element_table(p, geo.device)), -omega * mu, ptr(Ae),
+                                 stream_ptr()),
+        "pg_element_systems",
+    )
+    return Ae
+
+
+class AssemblyPlan:
+    """Symbolic phase (pattern, incidence lists, slot positions) for one mesh and order."""
+
+    def __init__(self, elems: ElementData, p: int, order="reference", row_range=None):
+        self.elems, self.p = elems, p
+        self.n = basis.ndof_element(p)
+        nEnt = elems.nEdges + (elems.nFaces if p >= 2 else 0) + (elems.T if p >= 3 else 0)
+        self.nEnt = nEnt
+        if isinstance(order, str):
+            if order == "reference":
+                order_host = None
+            elif order == "locality":
+                order_host = np.empty(nEnt, dtype=np.int32)
+                check(
+                    lib().pg_plan_locality_order(elems.T, p, ptr(elems.elemsE), ptr(elems.elemsF), elems.nEdges,
+                                                 elems.nFaces, ptr(order_host), stream_ptr()),
+                    "pg_plan_locality_order",
+                )
+            else:
+                raise ValueError("order must be 'reference', 'locality' or an int32 array")
+        else:
+            order_host = np.ascontiguousarray(order, dtype=np.int32)
+            if order_host.shape != (nEnt,):
+                raise ValueError("entity order must have %d entries" % nEnt)
+        self.order_host = order_host
+        rb, re_ = (0, -1) if row_range is None else row_range
+        handle = C.c_void_p()
+        check(
+            lib().pg_plan_create(elems.T, p, ptr(elems.elemsE), ptr(elems.elemsF), elems.nEdges, elems.nFaces,
+                                 ptr(order_host), rb, re_, C.byref(handle), stream_ptr()),
+            "pg_plan_create",
+        )
+        self._h = handle
+        L = lib()
+        self.N = L.pg_plan_num_dofs(handle)
+        self.local_rows = L.pg_plan_local_rows(handle)
+        self.row_begin = L.pg_plan_row_begin(handle)
+        self.nnz = L.pg_plan_nnz(handle)
+        self.contributions = L.pg_plan_contributions(handle)
+        self.max_row_length = L.pg_plan_max_row_length(handle)
+        self._csr = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().pg_plan_destroy(h)
+            except Exception:
+                pass
+
+    def csr(self):
+        """(rowptr int64 [rows+1], colidx int32 [nnz]) of the owned rows."""
+        if self._csr is None:
+            dev = self.elems.device
+            rowptr = torch.empty((self.local_rows + 1,), dtype=torch.int64, device=dev)
+            colidx = torch.empty((max(self.nnz, 1),), dtype=torch.int32, device=dev)[: self.nnz]
+            check(lib().pg_plan_csr(self._h, ptr(rowptr), ptr(colidx), stream_ptr()), "pg_plan_csr")
+            self._csr = (rowptr, colidx)
+        return self._csr
+
+    def dof_permutation(self) -> torch.Tensor:
+        """perm[ref_dof] = index in the numbering in use."""
+        perm = torch.empty((self.N,), dtype=torch.int32, device=self.elems.device)
+        check(lib().pg_plan_dof_permutation(self._h, ptr(perm), stream_ptr()), "pg_plan_dof_permutation")
+        return perm
+
+    def entity_aligned_row(self, row: int) -> int:
+        return int(lib().pg_plan_entity_aligned_row(self._h, int(row)))
+
+    def set_dirichlet(self, bd_entity):
+        """bd_entity: [nEnt] uint8 (device tensor or host array) or None."""
+        if bd_entity is None:
+            check(lib().pg_plan_set_dirichlet(self._h, None, None, None, stream_ptr()), "pg_plan_set_dirichlet")
+            return
+        t = torch.as_tensor(bd_entity, dtype=torch.uint8).to(self.elems.device).contiguous()
+        if t.numel() != self.nEnt:
+            raise ValueError("bd_entity must have %d entries" % self.nEnt)
+        check(
+            lib().pg_plan_set_dirichlet(self._h, ptr(self.elems.elemsE), ptr(self.elems.elemsF), ptr(t), stream_ptr()),
+            "pg_plan_set_dirichlet",
+        )
+
+    def assemble(self, geo, code, omega, mu=MU0, apply_dirichlet=False, diag=1.0, out=None):
+        """Numeric phase -> vals [nnz] complex128."""
+        dev = self.elems.device
+        vals = out if out is not None else torch.empty((max(self.nnz, 1),), dtype=torch.complex128, device=dev)[: self.nnz]
+        check(
+            lib().pg_assemble(self._h, ptr(geo), ptr(code), ptr(element_table(self.p, dev)), -omega * mu,
+                              1 if apply_dirichlet else 0, float(diag), ptr(vals), stream_ptr()),
+            "pg_assemble",
+        )
+        return vals
+
+
+class CSRMatrix:
+    """Complex128 CSR block of owned rows [row_begin, row_begin+rows) x N columns."""
+
+    def __init__(self, rowptr, colidx, vals, N, row_begin=0):
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.N, self.row_begin = int(N), int(row_begin)
+        self.rows = int(rowptr.numel() - 1)
+        self.nnz = int(vals.numel())
+
+    def mult(self, x: torch.Tensor, y: torch.Tensor = None) -> torch.Tensor:
+        """y = A x  (MatMult); x has N entries, y the owned rows."""
+        if y is None:
+            y = torch.empty((self.rows,), dtype=torch.complex128, device=x.device)
+        check(
+            lib().pg_spmv(self.rows, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x), ptr(y), stream_ptr()),
+            "pg_spmv",
+        )
+        return y
+
+    def diagonal(self) -> torch.Tensor:
+        d = torch.empty((self.rows,), dtype=torch.complex128, device=self.vals.device)
+        check(
+            lib().pg_csr_diagonal(self.rows, self.row_begin, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(d),
+                                  stream_ptr()),
+            "pg_csr_diagonal",
+        )
+        return d
+
+    def zeroRowsColumns(self, bd_rows, diag: float = 1.0):
+        """A.zeroRowsColumns(rows) (solver.py:562): rows given as global dof ids."""
+        mask = torch.zeros((self.N,), dtype=torch.uint8, device=self.vals.device)
+        idx = torch.as_tensor(np.asarray(bd_rows, dtype=np.int64), device=self.vals.device)
+        mask[idx] = 1
+        check(
+            lib().pg_zero_rows_columns(self.rows, self.row_begin, ptr(self.rowptr), ptr(self.colidx), ptr(mask),
+                                       float(diag), ptr(self.vals), stream_ptr()),
+            "pg_zero_rows_columns",
+        )
+
+    def spmv_bytes(self) -> int:
+        """Algorithmic bytes of one SpMV: 20 nnz + 40 rows."""
+        return 20 * self.nnz + 40 * self.rows
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix(
+            (self.vals.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()), shape=(self.rows, self.N)
+        )
+
+
+__all__ = [
+    "ElementData", "AssemblyPlan", "CSRMatrix", "element_table", "element_matrices", "element_systems", "MU0",
+    "PetgemB200Error",
+]

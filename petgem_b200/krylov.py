@@ -1,0 +1,323 @@
+"""Krylov drivers (restarted GMRES, BiCGStab) over the C-ABI vector kernels.
+
+Stands in for ``ksp.solve(b, x)`` at ``petgem/solver.py:584-590`` with the PETSc
+defaults that apply silently there: GMRES restart 30, LEFT
+preconditioning, classical Gram-Schmidt (one VecMDot + one VecMAXPY per
+iteration), zero initial guess, convergence on the preconditioned residual norm
+relative to ||M^-1 b||, maxit 10000.  Host code is Python; every vector operation
+is a kernel from include/petgem_b200.h working on device scalars.  With a process
+group, rows are owned PETSc-style by contiguous blocks: the SpMV input is
+all-gathered over NCCL and the dot products are all-reduced.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .device import CSRMatrix
+
+_C128 = torch.complex128
+
+
+class DistContext:
+    """Row-block ownership across ranks (PETSc-style contiguous blocks, entity aligned)."""
+
+    def __init__(self, row_begins, N, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.row_begins = [int(r) for r in row_begins] + [int(N)]
+        self.N = int(N)
+        self.sizes = [self.row_begins[i + 1] - self.row_begins[i] for i in range(self.world)]
+        self.max_rows = max(self.sizes)
+
+    def remap_columns(self, colidx: torch.Tensor) -> torch.Tensor:
+        """Global column -> index in the padded all-gather buffer [world, max_rows]."""
+        starts = torch.tensor(self.row_begins[:-1], dtype=torch.int64, device=colidx.device)
+        c = colidx.to(torch.int64)
+        owner = torch.bucketize(c, starts, right=True) - 1
+        return (owner * self.max_rows + (c - starts[owner])).to(torch.int32)
+
+    def gather(self, local: torch.Tensor, padded_send: torch.Tensor, full: torch.Tensor) -> torch.Tensor:
+        padded_send[: local.numel()].copy_(local)
+        self.dist.all_gather_into_tensor(torch.view_as_real(full).view(-1), torch.view_as_real(padded_send).view(-1),
+                                         group=self.group)
+        return full
+
+    def allreduce(self, t: torch.Tensor) -> None:
+        self.dist.all_reduce(torch.view_as_real(t), op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class Operator:
+    """y = M^-1 A x on the owned rows, with the halo handled for the caller."""
+
+    def __init__(self, A: CSRMatrix, pc: str = "none", ctx: DistContext = None):
+        self.A, self.ctx = A, ctx
+        self.n = A.rows
+        dev = A.vals.device
+        self.pc = pc
+        self.inv_diag = None
+        if pc == "jacobi":
+            d = A.diagonal()
+            self.inv_diag = torch.where(d == 0, torch.ones_like(d), 1.0 / d)  # PCJACOBI: zero diagonal -> 1
+        elif pc != "none":
+            raise ValueError("unsupported preconditioner %r (none, jacobi)" % pc)
+        if ctx is not None and ctx.world > 1:
+            self.colidx_local = ctx.remap_columns(A.colidx)
+            self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
+            self.full = torch.zeros((ctx.world * ctx.max_rows,), dtype=_C128, device=dev)
+            self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin)
+        self.spmv_calls = 0
+
+    def matvec(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.gather(x, self.send, self.full)
+            self.A_halo.mult(self.full, y)
+        else:
+            self.A.mult(x, y)
+        self.spmv_calls += 1
+        return y
+
+    def precond(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.inv_diag is None:
+            if y.data_ptr() != x.data_ptr():
+                y.copy_(x)
+        else:
+            check(lib().pg_zpointwise_mult(self.n, ptr(x), ptr(self.inv_diag), ptr(y), stream_ptr()), "pg_zpointwise_mult")
+        return y
+
+    def apply(self, x, y, tmp):
+        """y = M^-1 (A x)."""
+        self.matvec(x, tmp)
+        return self.precond(tmp, y)
+
+
+class VecKernels:
+    """Thin wrappers over the BLAS-1 entry points; results stay on the device."""
+
+    def __init__(self, n, device, ctx: DistContext = None, kmax=32):
+        self.n, self.ctx = int(n), ctx
+        self.work = torch.empty((lib().pg_reduce_workspace_bytes(kmax) // 16,), dtype=_C128, device=device)
+        self.dev = device
+
+    def mdot(self, k, V, ldv, w, out):
+        check(lib().pg_zmdotc(self.n, k, ptr(V), ldv, ptr(w), ptr(out), ptr(self.work), stream_ptr()), "pg_zmdotc")
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.allreduce(out[:k])
+        return out
+
+    def dot(self, x, y, out):
+        """out[0] = sum conj(x) y."""
+        check(lib().pg_zdotc(self.n, ptr(x), ptr(y), ptr(out), ptr(self.work), stream_ptr()), "pg_zdotc")
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.allreduce(out[:1])
+        return out
+
+    def nrm2sq(self, x, out):
+        check(lib().pg_dznrm2sq(self.n, ptr(x), ptr(out), ptr(self.work), stream_ptr()), "pg_dznrm2sq")
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.allreduce(out[:1])
+        return out
+
+    def maxpy(self, k, alpha, scale, V, ldv, w):
+        check(lib().pg_zmaxpy(self.n, k, ptr(alpha), float(scale), ptr(V), ldv, ptr(w), stream_ptr()), "pg_zmaxpy")
+
+    def axpy(self, alpha, x, y):
+        check(lib().pg_zaxpy(self.n, ptr(alpha), ptr(x), ptr(y), stream_ptr()), "pg_zaxpy")
+
+    def aypx(self, beta, x, y):
+        check(lib().pg_zaypx(self.n, ptr(beta), ptr(x), ptr(y), stream_ptr()), "pg_zaypx")
+
+    def axpbypcz(self, a, x, b, y, c, z, w):
+        check(lib().pg_zaxpbypcz(self.n, ptr(a), ptr(x), ptr(b), ptr(y), ptr(c), ptr(z), ptr(w), stream_ptr()),
+              "pg_zaxpbypcz")
+
+    def scal(self, alpha, x, inv_real=False):
+        check(lib().pg_zscal(self.n, ptr(alpha), 1 if inv_real else 0, ptr(x), stream_ptr()), "pg_zscal")
+
+
+class SolveResult:
+    def __init__(self, x, iterations, residuals, converged, reason):
+        self.x, self.iterations, self.residuals = x, iterations, residuals
+        self.converged, self.reason = converged, reason
+
+
+def gmres(op: Operator, b: torch.Tensor, rtol=1e-8, restart=30, maxit=10000, atol=1e-50, x0=None, monitor=None):
+    """Left-preconditioned GMRES(restart), classical Gram-Schmidt (KSPGMRES defaults)."""
+    n, dev = op.n, b.device
+    vk = VecKernels(n, dev, op.ctx, kmax=restart + 2)
+    V = torch.zeros((restart + 1, n), dtype=_C128, device=dev)
+    w = torch.empty((n,), dtype=_C128, device=dev)
+    tmp = torch.empty((n,), dtype=_C128, device=dev)
+    x = torch.zeros((n,), dtype=_C128, device=dev) if x0 is None else x0.clone()
+    hcol = torch.zeros((restart + 2,), dtype=_C128, device=dev)
+    ycoef = torch.zeros((restart + 1,), dtype=_C128, device=dev)
+    one = torch.ones((1,), dtype=_C128, device=dev)
+    minus_one = -one
+    scal = torch.zeros((2,), dtype=_C128, device=dev)
+
+    op.precond(b, tmp)
+    bnorm = math.sqrt(vk.nrm2sq(tmp, scal)[0].real.item())
+    if bnorm == 0.0:
+        return SolveResult(x, 0, [0.0], True, "zero rhs")
+    tol = max(rtol * bnorm, atol)
+    its, hist = 0, []
+    x_is_zero = x0 is None
+    while True:
+        # r = M^-1 (b - A x)
+        if x_is_zero:
+            op.precond(b, V[0])
+        else:
+            op.matvec(x, tmp)
+            vk.axpbypcz(one, b, minus_one, tmp, None, None, tmp)
+            op.precond(tmp, V[0])
+        beta = math.sqrt(vk.nrm2sq(V[0], scal)[0].real.item())
+        if not hist:
+            hist.append(beta)
+            if monitor:
+                monitor(0, beta)
+        if beta <= tol:
+            return SolveResult(x, its, hist, True, "rtol")
+        if its >= maxit:
+            return SolveResult(x, its, hist, False, "maxit")
+        scal[1] = beta
+        vk.scal(scal[1:], V[0], inv_real=True)
+        H = np.zeros((restart + 1, restart), dtype=np.complex128)
+        g = np.zeros(restart + 1, dtype=np.complex128)
+        g[0] = beta
+        cs = np.zeros(restart)
+        sn = np.zeros(restart, dtype=np.complex128)
+        k = 0
+        while k < restart and its < maxit:
+            op.apply(V[k], w, tmp)                     # w = M^-1 A v_k
+            vk.mdot(k + 1, V, n, w, hcol)              # h_0..k = V^H w   (VecMDot)
+            vk.maxpy(k + 1, hcol, -1.0, V, n, w)       # w -= sum h_i v_i (VecMAXPY)
+            vk.nrm2sq(w, hcol[k + 1:k + 2])
+            hcol[k + 1] = torch.sqrt(hcol[k + 1].real)
+            V[k + 1].copy_(w)
+            vk.scal(hcol[k + 1:k + 2], V[k + 1], inv_real=True)
+            h = hcol[: k + 2].cpu().numpy()            # the one host sync of the iteration
+            for i in range(k):                         # previous Givens rotations
+                t = cs[i] * h[i] + sn[i] * h[i + 1]
+                h[i + 1] = -np.conj(sn[i]) * h[i] + cs[i] * h[i + 1]
+                h[i] = t
+            a_, b_ = h[k], h[k + 1]
+            den = math.sqrt(abs(a_) ** 2 + abs(b_) ** 2)
+            if abs(a_) == 0.0:
+                cs[k], sn[k] = 0.0, 1.0
+            else:
+                cs[k] = abs(a_) / den
+                sn[k] = (a_ / abs(a_)) * np.conj(b_) / den
+            h[k] = cs[k] * a_ + sn[k] * b_
+            h[k + 1] = 0.0
+            H[: k + 2, k] = h
+            g[k + 1] = -np.conj(sn[k]) * g[k]
+            g[k] = cs[k] * g[k]
+            k += 1
+            its += 1
+            res = abs(g[k])
+            hist.append(res)
+            if monitor:
+                monitor(its, res)
+            if res <= tol or b_ == 0.0:
+                break
+        y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
+        ycoef[:k] = torch.from_numpy(y).to(dev)
+        vk.maxpy(k, ycoef, 1.0, V, n, x)               # x += V y
+        x_is_zero = False
+        if hist[-1] <= tol:
+            return SolveResult(x, its, hist, True, "rtol")
+
+
+def bicgstab(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None):
+    """Left-preconditioned BiCGStab (KSPBCGS)."""
+    n, dev = op.n, b.device
+    vk = VecKernels(n, dev, op.ctx, kmax=4)
+    z = lambda: torch.zeros((n,), dtype=_C128, device=dev)  # noqa: E731
+    x, r, rhat, p_, v, s, t, tmp = z(), z(), z(), z(), z(), z(), z(), z()
+    sc = torch.zeros((8,), dtype=_C128, device=dev)
+    one = torch.ones((1,), dtype=_C128, device=dev)
+    op.precond(b, r)
+    bnorm = math.sqrt(vk.nrm2sq(r, sc)[0].real.item())
+    if bnorm == 0.0:
+        return SolveResult(x, 0, [0.0], True, "zero rhs")
+    tol = max(rtol * bnorm, atol)
+    rhat.copy_(r)
+    rho = alpha = omega = 1.0 + 0.0j
+    hist = [bnorm]
+    for it in range(1, maxit + 1):
+        rho_new = complex(vk.dot(rhat, r, sc)[0].item())
+        if rho_new == 0.0:
+            return SolveResult(x, it - 1, hist, False, "breakdown rho")
+        beta = (rho_new / rho) * (alpha / omega)
+        # p = r + beta (p - omega v)
+        sc[1], sc[2] = beta, -beta * omega
+        vk.axpbypcz(one, r, sc[1:2], p_, sc[2:3], v, p_)
+        op.apply(p_, v, tmp)
+        den = complex(vk.dot(rhat, v, sc)[0].item())
+        if den == 0.0:
+            return SolveResult(x, it - 1, hist, False, "breakdown alpha")
+        alpha = rho_new / den
+        sc[1] = -alpha
+        vk.axpbypcz(one, r, sc[1:2], v, None, None, s)     # s = r - alpha v
+        op.apply(s, t, tmp)
+        vk.dot(t, s, sc[3:4])
+        vk.nrm2sq(t, sc[4:5])
+        ts, tt = complex(sc[3].item()), sc[4].real.item()
+        if tt == 0.0:
+            return SolveResult(x, it - 1, hist, False, "breakdown omega")
+        omega = ts / tt
+        sc[1], sc[2] = alpha, omega
+        vk.axpy(sc[1:2], p_, x)
+        vk.axpy(sc[2:3], s, x)
+        sc[1] = -omega
+        vk.axpbypcz(one, s, sc[1:2], t, None, None, r)     # r = s - omega t
+        rho = rho_new
+        res = math.sqrt(vk.nrm2sq(r, sc)[0].real.item())
+        hist.append(res)
+        if monitor:
+            monitor(it, res)
+        if res <= tol:
+            return SolveResult(x, it, hist, True, "rtol")
+    return SolveResult(x, maxit, hist, False, "maxit")
+
+
+def parse_petsc_options(path_or_text):
+    """Read the PETSc options file passed on the PETGEM command line
+    (kernel.py:15, examples/case1/petsc.opts) -> dict of the options we honour."""
+    import os
+
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    opts = {}
+    for line in text.splitlines():
+        line = line.split("#", 1)[0].strip()
+        if not line.startswith("-"):
+            continue
+        parts = line.split()
+        opts[parts[0][1:]] = parts[1] if len(parts) > 1 else True
+    return opts
+
+
+def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, monitor=None) -> SolveResult:
+    """KSP front end: ksp_type gmres|bcgs, pc_type none|jacobi (sor is mapped to jacobi
+    with a warning: PETSc's SOR sweep is sequential), ksp_rtol,
+    ksp_gmres_restart, ksp_max_it."""
+    o = dict(options or {})
+    ksp = str(o.get("ksp_type", "gmres"))
+    pc = str(o.get("pc_type", "jacobi"))
+    if pc in ("sor", "bjacobi", "asm", "gamg", "lu", "ilu"):
+        pc = "jacobi"
+    rtol = float(o.get("ksp_rtol", 1e-5))  # PETSc default when the file does not set it
+    maxit = int(o.get("ksp_max_it", 10000))
+    op = Operator(A, pc=pc, ctx=ctx)
+    if ksp == "gmres":
+        return gmres(op, b, rtol=rtol, restart=int(o.get("ksp_gmres_restart", 30)), maxit=maxit, monitor=monitor)
+    if ksp in ("bcgs", "bicgstab"):
+        return bicgstab(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
+    raise ValueError("unsupported ksp_type %r (gmres, bcgs)" % ksp)
