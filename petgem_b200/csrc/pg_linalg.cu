@@ -285,7 +285,7 @@ int pg_spmv(int64_t rows, const int64_t *rowptr, const int32_t *colidx, const do
             double *y, void *stream) {
     PG_REQUIRE(rows >= 0, PG_EINVAL, "pg_spmv: rows < 0");
     if (rows == 0) return PG_OK;
-    PG_REQUIRE(rowptr && colidx && vals && x && y, PG_EINVAL, "pg_spmv: null pointer");
+    PG_REQUIRE(rowptr && x && y, PG_EINVAL, "pg_spmv: null pointer");  // colidx/vals may be null when nnz == 0
     cudaStream_t st = (cudaStream_t)stream;
     // lanes per row from the mean row length (host knows it only through the caller: use 16,
     // the best trade-off for the 15..120 nnz/row of p=1..2; long rows are still coalesced)

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256)
         const int L = rowlen[g];
         const int64_t v0 = valoff[b - b0];
         const int64_t row0 = row_base[b] - row_begin;
-        if (lane < r) rowptr[row0 + lane] = v0 + (int64_t)lane * L;
+        for (int d = lane; d < r; d += 32) rowptr[row0 + d] = v0 + (int64_t)d * L;
         const int64_t c0 = colent_ptr[g];
         const int nc = (int)(colent_ptr[g + 1] - c0);
         int posbase = 0;

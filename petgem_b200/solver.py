@@ -1,0 +1,200 @@
+"""Drop-in ``Solver`` for the B200 path: same call sequence as ``petgem/solver.py``
+(``kernel.py:64-73``): ``Solver().setup(inputSetup)``, ``.assembly(inputSetup)``,
+``.run(inputSetup)``.
+
+setup    reads the scratch files of ``Preprocessing`` (solver.py:66-123) and moves
+         the per-element rows to HBM once;
+assembly replaces the Python element loop + MatSetValues (solver.py:191-235) by the
+         geometry kernel and the fused element-matrix / row-gather kernel, and
+         builds the CSEM right-hand side (solver.py:247-316) for the one source
+         element on the host;
+run      applies MatZeroRowsColumns (solver.py:562-574) and solves with the Krylov
+         drivers configured from the PETSc options file (solver.py:584-590), then
+         writes ``x{i}.dat`` (solver.py:593-594) for ``Postprocessing``.
+Leaves ``self.A``, ``self.b[i]``, ``self.x[i]`` like the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import hvfem, krylov
+from .common import Print, Timers
+from .parallel import (MPIEnvironment, createParallelMatrix, createParallelVector, readPetscMatrix,
+                       readPetscVector, writePetscVector)
+
+
+class Solver():
+    """Class for solver."""
+
+    def __init__(self):
+        self.petsc_options = {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": "1e-8"}
+        self.ksp_results = []
+
+    def setOptions(self, options):
+        """Options of the PETSc options file given on the command line (kernel.py:15)."""
+        self.petsc_options = dict(options)
+
+    # ------------------------------------------------------------------------------
+    def setup(self, inputSetup):
+        Timers()["Setup"].start()
+        output = inputSetup.output
+        out_dir = output.get('directory_scratch')
+        Print.master('     Importing files')
+        parEnv = MPIEnvironment()
+
+        def real_table(name, dtype):
+            return np.ascontiguousarray(readPetscMatrix(out_dir + '/' + name).array.real.astype(dtype))
+
+        self.nodes = real_table('nodes.dat', np.float64)                # [T,12]
+        self.elemsN = real_table('meshConnectivity.dat', np.int32)      # [T,4]
+        self.elemsE = real_table('edges.dat', np.int32)                 # [T,6]
+        self.edgesNodes = real_table('edgesNodes.dat', np.int32)        # [T,12]
+        self.elemsF = real_table('faces.dat', np.int32)                 # [T,4]
+        self.facesEdges = real_table('facesEdges.dat', np.int32)        # [T,12]
+        self.dofs = real_table('dofs.dat', np.int64)                    # [T,n]
+        self.sigmaModel = real_table('conductivityModel.dat', np.float64)
+        tmp = readPetscVector(out_dir + '/nnz.dat')
+        self.nnz = tmp.getArray().real.astype(np.int64)
+        self.total_num_dofs = tmp.getSizes()[1]
+        mode = inputSetup.model.get('mode')
+        if mode == 'csem':
+            self.boundaries = readPetscVector(out_dir + '/boundaries.dat')
+            if parEnv.rank == 0:
+                self.source_data = readPetscVector(out_dir + '/source.dat')
+        elif mode == 'mt':
+            self.boundaries = readPetscMatrix(out_dir + '/boundaryElements.dat')
+
+        # consistency of the numbering the kernels rebuild from (edges.dat, faces.dat)
+        p = inputSetup.run.get('nord')
+        nE, nF = int(self.elemsE.max()) + 1, int(self.elemsF.max()) + 1
+        k = min(64, self.dofs.shape[0])
+        ref = hvfem.dofs_of_elements(self.elemsE[:k], self.elemsF[:k], np.arange(k), nE, nF, p)
+        if not np.array_equal(self.dofs[:k], ref):
+            Print.master('     dofs.dat is not consistent with edges.dat/faces.dat')
+            exit(-1)
+
+        from .device import ElementData
+        self.elems = ElementData(self.nodes, self.elemsN, self.elemsE, self.edgesNodes, self.facesEdges, self.elemsF,
+                                 self.sigmaModel, nE, nF)
+        Timers()["Setup"].stop()
+        return
+
+    # ------------------------------------------------------------------------------
+    def assembly(self, inputSetup):
+        import torch
+
+        from .device import MU0, AssemblyPlan, CSRMatrix
+
+        Timers()["Assembly"].start()
+        model, run = inputSetup.model, inputSetup.run
+        Print.master('     Assembling linear system')
+        parEnv = MPIEnvironment()
+        basis_order = run.get('nord')
+        num_polarizations = run.get('num_polarizations')
+        mode = model.get('mode')
+        data_model = model.get(mode)
+        frequency = data_model.get('source').get('frequency') if mode == 'csem' else data_model.get('frequency')
+        omega = frequency * 2. * np.pi
+        mu = MU0
+        Const = 1j * omega * mu
+        self.omega, self.mu = omega, mu
+
+        # ---- LHS: symbolic phase once, numeric phase fused (solver.py:188-235) ----
+        order = run.get('b200_order', 'locality')
+        self.plan = AssemblyPlan(self.elems, basis_order, order=order)
+        if self.plan.N != self.total_num_dofs:
+            Print.master('     Number of DOFs is not consistent')
+            exit(-1)
+        geo, code = self.elems.geometry()
+        vals = self.plan.assemble(geo, code, omega, mu)
+        rowptr, colidx = self.plan.csr()
+        self.A = createParallelMatrix(self.total_num_dofs, self.total_num_dofs, self.nnz, run.get('cuda'))
+        self.A.plan = self.plan
+        self.A.csr = CSRMatrix(rowptr, colidx, vals, self.plan.N)
+        self.A.perm = self.plan.dof_permutation() if order != 'reference' else None
+
+        # ---- RHS ----
+        self.b, self.x = [], []
+        for i in np.arange(num_polarizations):
+            self.b.append(createParallelVector(self.total_num_dofs, run.get('cuda')))
+            self.x.append(createParallelVector(self.total_num_dofs, run.get('cuda')))
+        if mode == 'csem':
+            src = data_model.get('source')
+            position = np.asarray(src.get('position'), dtype=np.float64)
+            rot = hvfem.computeSourceVectorRotation(src.get('azimuth'), src.get('dip'))
+            moment = src.get('current') * src.get('length')
+            field = rot[0] * np.array([moment, 0., 0.]) + rot[1] * np.array([0., moment, 0.]) \
+                + rot[2] * np.array([0., 0., moment])
+            if parEnv.rank == 0:
+                sd = self.source_data.getArray().real
+                nodesEle = sd[0:4].astype(np.int64)
+                coordEle = sd[4:16].reshape(4, 3)
+                edgesFace = sd[20:32].astype(np.int64).reshape(4, 3)
+                edgesEle = sd[32:38].astype(np.int64)
+                edgesNodesEle = sd[38:50].astype(np.int64).reshape(6, 2)
+                dofsSource = sd[50:].astype(np.int64)
+                jacobian, invjacobian = hvfem.computeJacobian(coordEle)
+                eo, fo = hvfem.computeElementOrientation(edgesEle, nodesEle, edgesNodesEle, edgesFace)
+                XiEtaZeta = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, position)
+                basis, _ = hvfem.computeBasisFunctions(eo, fo, jacobian, invjacobian, basis_order, XiEtaZeta)
+                rhs_contribution = np.matmul(field, basis[:, :, 0]) * Const
+                self.b[0].setValues(dofsSource, rhs_contribution, addv=True)
+        elif mode == 'mt':
+            Print.master('     MT boundary right-hand side (solver.py:318-512) is outside the B200 hot path: '
+                         'assemble b with the reference and pass it through b{i}.dat')
+            import os
+            out_dir = inputSetup.output.get('directory_scratch')
+            for i in np.arange(num_polarizations):
+                path = out_dir + '/b' + str(i) + '.dat'
+                if not os.path.exists(path):
+                    Print.master('     missing ' + path)
+                    exit(-1)
+                self.b[i].t.copy_(torch.as_tensor(readPetscVector(path).getArray(), device=self.b[i].t.device))
+        for i in np.arange(num_polarizations):
+            self.b[i].assemblyBegin()
+            self.b[i].assemblyEnd()
+        torch.cuda.synchronize()
+        Timers()["Assembly"].stop()
+        return
+
+    # ------------------------------------------------------------------------------
+    def run(self, inputSetup):
+        import torch
+
+        model, run, output = inputSetup.model, inputSetup.run, inputSetup.output
+        out_dir = output.get('directory_scratch')
+        num_polarizations = run.get('num_polarizations')
+        mode = model.get('mode')
+        Print.master('     Solving linear system')
+        if mode == 'csem':
+            Timers()["SetBoundaries"].start()
+            bd = np.real(self.boundaries.getArray()).astype(np.int64)
+            self.A.zeroRowsColumns(bd)                                   # solver.py:562
+            self.b[0].setValues(bd, np.zeros(bd.size, dtype=np.complex128))  # solver.py:565-567
+            self.A.assemblyBegin()
+            self.A.assemblyEnd()
+            Timers()["SetBoundaries"].stop()
+
+        Timers()["Solver"].start()
+        self.ksp_results = []
+        perm = self.A.perm.to(torch.int64) if self.A.perm is not None else None
+        for i in np.arange(num_polarizations):
+            b = self.b[i].t
+            if perm is not None:
+                bi = torch.empty_like(b)
+                bi[perm] = b
+            else:
+                bi = b
+            res = krylov.solve(self.A.csr, bi, self.petsc_options)      # ksp.solve(b, x), solver.py:589
+            self.ksp_results.append(res)
+            self.x[i].t.copy_(res.x[perm] if perm is not None else res.x)
+            if not res.converged:
+                Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
+            writePetscVector(out_dir + '/x' + str(i) + '.dat', self.x[i])
+        torch.cuda.synchronize()
+        Timers()["Solver"].stop()
+        return
+
+
+def unitary_test():
+    """Unitary test for solver.py script."""

@@ -1,0 +1,496 @@
+"""Parity of the CUDA hot path (through the C ABI) against the oracle and the
+reference-derived golden fixtures.  Integer work (orientation codes, DOF numbering,
+CSR pattern) must be bit-exact; element / global values within 1e-12 norm-relative
+(north_star); Krylov solutions within 1e-6 of a direct solve.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12  # north_star tolerance for element and global matrix values (norm-relative)
+
+
+def _elems_from_topo(topo, sigma=None):
+    from petgem_b200.device import ElementData
+
+    T = topo["elemsN"].shape[0]
+    if sigma is None:
+        sig = np.array([1.0, 0.01, 1.0, 3.3333])[topo["tags"] - 1]
+        sigma = np.stack([sig, sig], axis=1)
+    return ElementData.from_mesh(topo["nodes"], topo["elemsN"], topo["elemsE"], topo["edgesNodes"], topo["elemsF"],
+                                 topo["facesE"], sigma)
+
+
+def _fake_connectivity(eo, fo):
+    """Per-element rows that make computeElementOrientation return the given codes."""
+    cnt = eo.shape[0]
+    loc_e = [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+    loc_f = [(0, 1, 2), (0, 4, 3), (1, 5, 4), (2, 5, 3)]
+    k12 = {0: (1, 2), 1: (3, 1), 2: (2, 3), 3: (3, 2), 4: (1, 3), 5: (2, 1)}
+    elemsN = np.tile(np.array([10, 11, 12, 13]), (cnt, 1))
+    elemsE = np.tile(np.arange(6), (cnt, 1))
+    edgesNodes = np.zeros((cnt, 6, 2), dtype=np.int64)
+    facesEdges = np.zeros((cnt, 4, 3), dtype=np.int64)
+    for i in range(cnt):
+        for e, (a, b) in enumerate(loc_e):
+            edgesNodes[i, e] = (10 + b, 10 + a) if eo[i, e] else (10 + a, 10 + b)
+        for f, le in enumerate(loc_f):
+            k1, k2 = k12[int(fo[i, f])]
+            k3 = 6 - k1 - k2
+            facesEdges[i, f, k1 - 1], facesEdges[i, f, k2 - 1], facesEdges[i, f, k3 - 1] = le[0], le[1], le[2]
+    return elemsN, elemsE, edgesNodes.reshape(cnt, 12), facesEdges.reshape(cnt, 12)
+
+
+def test_geometry_orientation_codes_bit_exact(topo):
+    from petgem_b200 import hvfem
+
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    eo, fo = hvfem.unpack_orientation(code.cpu().numpy())
+    assert np.array_equal(np.concatenate([eo, fo], axis=1), topo["orient"])
+    # geometric factors against numpy (computeJacobian + inv + det)
+    X = topo["nodes"][topo["elemsN"]]
+    J = X[:, 1:] - X[:, :1]
+    sig = np.array([1.0, 0.01, 1.0, 3.3333])[topo["tags"] - 1]
+    ref = hvfem.geometric_factors(J, np.stack([sig, sig], axis=1))
+    g = geo.cpu().numpy()
+    assert np.abs(g - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_element_matrices_match_reference(p):
+    """GPU computeElementalMatrices vs the UNMODIFIED reference's Me/Ke (golden): random tets,
+    all face codes, flipped edges, negative detJ, VTI sigma."""
+    from petgem_b200 import device as dv
+
+    g = golden("hvfem_elemental_p%d.npz" % p)
+    cnt = g["coords"].shape[0]
+    elemsN, elemsE, edgesNodes, facesEdges = _fake_connectivity(g["eo"], g["fo"])
+    el = dv.ElementData(g["coords"].reshape(cnt, 12), elemsN, elemsE, edgesNodes, facesEdges,
+                        np.zeros((cnt, 4), dtype=np.int32), g["sigma"], 6, 4)
+    geo, code = el.geometry()
+    from petgem_b200 import hvfem
+    eo, fo = hvfem.unpack_orientation(code.cpu().numpy())
+    assert np.array_equal(eo, g["eo"]) and np.array_equal(fo, g["fo"])
+    Me, Ke = dv.element_matrices(p, geo, code)
+    Me, Ke = Me.cpu().numpy(), Ke.cpu().numpy()
+    for i in range(cnt):
+        assert np.abs(Me[i] - g["Me"][i]).max() <= REL * np.abs(g["Me"][i]).max(), (p, i)
+        assert np.abs(Ke[i] - g["Ke"][i]).max() <= REL * np.abs(g["Ke"][i]).max(), (p, i)
+        assert np.array_equal(Me[i], Me[i].T) or np.abs(Me[i] - Me[i].T).max() <= 1e-15 * np.abs(Me[i]).max()
+    if cnt >= 3:
+        assert (np.linalg.det(g["coords"][:, 1:] - g["coords"][:, :1]) < 0).any()  # signed detJ exercised
+
+
+def test_single_element_api_matches_reference():
+    """petgem.hvfem.computeElementalMatrices signature, one element, routed to the GPU."""
+    from petgem_b200 import hvfem
+
+    g = golden("hvfem_elemental_p2.npz")
+    for i in (0, 2, 5):
+        J, Ji = hvfem.computeJacobian(g["coords"][i])
+        Me, Ke = hvfem.computeElementalMatrices(g["eo"][i], g["fo"][i], J, Ji, 2, g["sigma"][i])
+        assert np.abs(Me - g["Me"][i]).max() <= REL * np.abs(g["Me"][i]).max()
+        assert np.abs(Ke - g["Ke"][i]).max() <= REL * np.abs(g["Ke"][i]).max()
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_element_systems_on_reference_mesh(topo, p):
+    from petgem_b200 import device as dv
+
+    g = golden("test_mesh_elements_p%d.npz" % p)
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    sel = torch.as_tensor(g["sel"].astype(np.int64), device=geo.device)
+    Ae = dv.element_systems(p, geo[sel].contiguous(), code[sel].contiguous(), float(g["omega"]), float(g["mu"]))
+    Ae = Ae.cpu().numpy()
+    for c in range(sel.numel()):
+        assert np.abs(Ae[c] - g["Ae"][c]).max() <= REL * np.abs(g["Ae"][c]).max()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_dof_numbering_bit_exact(topo, oracle, p):
+    el = _elems_from_topo(topo)
+    dofs = el.dofs(p).cpu().numpy()
+    ref, *_ = oracle.compute_connectivity_dofs(topo["elemsE"].astype(np.int64), topo["elemsF"].astype(np.int64), p)
+    assert np.array_equal(dofs, ref)
+    assert np.array_equal(dofs[topo["dofs_sel"]], topo["dofs_rows_p%d" % p])
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_csr_pattern_bit_exact(topo, oracle, p):
+    """Pattern = union of element cliques incl. explicit zeros, columns ascending (PETSc AIJ)."""
+    from petgem_b200.device import AssemblyPlan
+
+    el = _elems_from_topo(topo)
+    plan = AssemblyPlan(el, p)
+    rowptr, colidx = plan.csr()
+    dofs, *_, N = oracle.compute_connectivity_dofs(topo["elemsE"].astype(np.int64), topo["elemsF"].astype(np.int64), p)
+    rp, ci = oracle.csr_pattern(dofs, N)
+    assert plan.N == N and plan.nnz == ci.size
+    assert plan.nnz == {1: 189700, 2: 2681124, 3: 15227541}[p]  # SURVEY 6 [probe]
+    assert np.array_equal(rowptr.cpu().numpy(), rp)
+    assert np.array_equal(colidx.cpu().numpy(), ci)
+    assert plan.contributions == dofs.shape[0] * dofs.shape[1] ** 2
+    assert plan.max_row_length == int(np.diff(rp).max())
+
+
+def test_global_assembly_p1_matches_reference_loop(topo, oracle):
+    """Full test mesh, p=1: y = A x and diag(A) from the reference's own element loop (golden),
+    and every CSR value against the oracle's MatSetValues/ADD_VALUES restatement."""
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    g = golden("test_mesh_system_p1.npz")
+    omega, mu = float(g["omega"]), float(g["mu"])
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, 1)
+    vals = plan.assemble(geo, code, omega, mu)
+    rowptr, colidx = plan.csr()
+    A = CSRMatrix(rowptr, colidx, vals, plan.N)
+    x = torch.as_tensor(g["x"], device=vals.device)
+    y = A.mult(x).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= REL * np.abs(g["y"]).max()
+    d = A.diagonal().cpu().numpy()
+    assert np.abs(d - g["diag"]).max() <= REL * np.abs(g["diag"]).max()
+    # element values from the kernel -> oracle assembly -> same CSR values
+    from petgem_b200 import device as dv
+    Ae = dv.element_systems(1, geo, code, omega, mu).cpu().numpy()
+    dofs = topo["elemsE"].astype(np.int64)
+    rp, ci, v = oracle.assemble_global(Ae, dofs, plan.N)
+    assert np.array_equal(rp, rowptr.cpu().numpy()) and np.array_equal(ci, colidx.cpu().numpy())
+    assert np.abs(vals.cpu().numpy() - v).max() <= 1e-14 * np.abs(v).max()
+    # determinism: bit-identical on a second run
+    vals2 = plan.assemble(geo, code, omega, mu)
+    assert torch.equal(torch.view_as_real(vals), torch.view_as_real(vals2))
+
+
+def _small_case(m, seed=7, vti=0.5):
+    from petgem_b200 import synthetic
+    from petgem_b200.device import ElementData
+
+    nodes, elemsN = synthetic.kuhn_box(m, length=700.0, seed=seed)
+    tab = synthetic.mesh_tables(nodes, elemsN)
+    sigma = synthetic.layered_sigma(nodes, elemsN, vti_ratio=vti)
+    el = ElementData.from_mesh(nodes, elemsN, tab["elemsE"], tab["edgesNodes"], tab["elemsF"], tab["facesE"], sigma)
+    return tab, sigma, el
+
+
+def _oracle_system(oracle, tab, sigma, p, omega, mu):
+    nodes, elemsN = tab["nodes"], tab["elemsN"]
+    T = elemsN.shape[0]
+    n = p * (p + 2) * (p + 3) // 2
+    Ae = np.zeros((T, n, n), dtype=np.complex128)
+    for t in range(T):
+        Ae[t] = oracle.element_system(nodes[elemsN[t]], elemsN[t], tab["elemsE"][t],
+                                      tab["edgesNodes"][tab["elemsE"][t]], tab["facesE"][tab["elemsF"][t]],
+                                      sigma[t], p, omega, mu)
+    dofs, dof_edges, dof_faces, _, N = oracle.compute_connectivity_dofs(tab["elemsE"], tab["elemsF"], p)
+    rp, ci, v = oracle.assemble_global(Ae, dofs, N)
+    bd = oracle.compute_boundaries(dof_edges, dof_faces, tab["bEdges"], tab["bFaces"])
+    return rp, ci, v, bd, dofs, N
+
+
+@pytest.mark.parametrize("p,m", [(1, 4), (2, 3), (3, 3), (4, 2), (5, 2), (6, 1)])
+def test_fused_assembly_matches_oracle(oracle, p, m):
+    """Element loop + scatter-add fused on the GPU vs the oracle (VTI sigma, shuffled Kuhn box)."""
+    from petgem_b200.device import AssemblyPlan
+
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    tab, sigma, el = _small_case(m)
+    rp, ci, v, bd, dofs, N = _oracle_system(oracle, tab, sigma, p, omega, mu)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, p)
+    rowptr, colidx = plan.csr()
+    assert np.array_equal(rowptr.cpu().numpy(), rp) and np.array_equal(colidx.cpu().numpy(), ci)
+    vals = plan.assemble(geo, code, omega, mu).cpu().numpy()
+    assert np.abs(vals - v).max() <= REL * np.abs(v).max()
+    # explicit zeros are kept in the pattern
+    assert vals.size == ci.size
+
+
+@pytest.mark.parametrize("p,m", [(1, 4), (2, 3), (3, 2)])
+def test_dirichlet_fused_and_separate(oracle, p, m):
+    """A.zeroRowsColumns(boundary dofs) (solver.py:562): separate kernel and fused-in-assembly
+    both equal the oracle; pattern unchanged, diagonal 1."""
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    tab, sigma, el = _small_case(m)
+    rp, ci, v, bd, dofs, N = _oracle_system(oracle, tab, sigma, p, omega, mu)
+    vbc = oracle.zero_rows_columns(rp, ci, v, bd, 1.0)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, p)
+    rowptr, colidx = plan.csr()
+    vals = plan.assemble(geo, code, omega, mu)
+    A = CSRMatrix(rowptr, colidx, vals.clone(), plan.N)
+    A.zeroRowsColumns(bd, 1.0)
+    assert np.abs(A.vals.cpu().numpy() - vbc).max() <= REL * np.abs(v).max()
+    bd_entity = np.zeros(plan.nEnt, dtype=np.uint8)
+    bd_entity[tab["bEdges"]] = 1
+    if p >= 2:
+        bd_entity[tab["nEdges"] + tab["bFaces"]] = 1
+    plan.set_dirichlet(bd_entity)
+    fused = plan.assemble(geo, code, omega, mu, apply_dirichlet=True, diag=1.0).cpu().numpy()
+    assert np.abs(fused - vbc).max() <= REL * np.abs(v).max()
+    assert np.array_equal(fused == 0, A.vals.cpu().numpy() == 0)
+    # without the flag the plan still assembles the unconstrained matrix
+    again = plan.assemble(geo, code, omega, mu).cpu().numpy()
+    assert np.abs(again - v).max() <= REL * np.abs(v).max()
+
+
+@pytest.mark.parametrize("p,m", [(1, 4), (2, 3), (3, 2)])
+def test_locality_order_is_a_symmetric_permutation(p, m):
+    """Internal element-major numbering: A_int = P A_ref P^T with the permutation the plan reports."""
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    tab, sigma, el = _small_case(m)
+    geo, code = el.geometry()
+    ref = AssemblyPlan(el, p)
+    loc = AssemblyPlan(el, p, order="locality")
+    assert loc.N == ref.N and loc.nnz == ref.nnz
+    Aref = CSRMatrix(*ref.csr(), ref.assemble(geo, code, omega, mu), ref.N).to_scipy()
+    Aloc = CSRMatrix(*loc.csr(), loc.assemble(geo, code, omega, mu), loc.N).to_scipy()
+    perm = loc.dof_permutation().cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sort(perm), np.arange(ref.N))
+    assert np.array_equal(ref.dof_permutation().cpu().numpy(), np.arange(ref.N))
+    B = Aloc[perm][:, perm]  # B[i_ref, j_ref] = Aloc[perm[i_ref], perm[j_ref]]: back to reference numbering
+    B.sort_indices()
+    Aref.sort_indices()
+    assert np.array_equal(B.indptr, Aref.indptr) and np.array_equal(B.indices, Aref.indices)
+    assert np.abs(B.data - Aref.data).max() <= 1e-14 * np.abs(Aref.data).max()
+    cols = Aloc.indices
+    assert all(np.all(np.diff(cols[Aloc.indptr[i]:Aloc.indptr[i + 1]]) > 0) for i in range(0, ref.N, 7))
+
+
+def test_row_block_ownership_concatenates_to_global(topo):
+    """PETSc-style contiguous row blocks (entity aligned): per-rank plans tile the global CSR."""
+    from petgem_b200.device import AssemblyPlan
+
+    p = 2
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    full = AssemblyPlan(el, p, order="locality")
+    vfull = full.assemble(geo, code, omega, mu)
+    rp_full, ci_full = full.csr()
+    world = 3
+    cuts = [0] + [full.entity_aligned_row(full.N * r // world) for r in range(1, world)] + [full.N]
+    off = 0
+    for r in range(world):
+        part = AssemblyPlan(el, p, order=full.order_host, row_range=(cuts[r], cuts[r + 1]))
+        assert part.row_begin == cuts[r] and part.local_rows == cuts[r + 1] - cuts[r]
+        rp, ci = part.csr()
+        v = part.assemble(geo, code, omega, mu)
+        assert torch.equal(rp + off, rp_full[cuts[r]:cuts[r + 1] + 1])
+        assert torch.equal(ci, ci_full[off:off + part.nnz])
+        assert torch.equal(torch.view_as_real(v), torch.view_as_real(vfull[off:off + part.nnz]))
+        off += part.nnz
+    assert off == full.nnz
+    with pytest.raises(Exception):
+        AssemblyPlan(el, p, order=full.order_host, row_range=(1, full.N))  # not entity aligned at p=2
+
+
+def test_large_mesh_properties():
+    """Size-independent properties at a size the oracle cannot reach (~200k tets, p=2, 55M nnz):
+    run-to-run bit determinism, complex symmetry A = A^T (x^T A y == y^T A x), Dirichlet rows
+    are identity rows and fused == separate Dirichlet."""
+    from petgem_b200 import synthetic
+    from petgem_b200.device import AssemblyPlan, CSRMatrix, ElementData
+
+    m = 32
+    nodes, elemsN = synthetic.kuhn_box(m)
+    tab = synthetic.mesh_tables(nodes, elemsN)
+    sigma = synthetic.layered_sigma(nodes, elemsN)
+    el = ElementData.from_mesh(nodes, elemsN, tab["elemsE"], tab["edgesNodes"], tab["elemsF"], tab["facesE"], sigma)
+    geo, code = el.geometry()
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    plan = AssemblyPlan(el, 2, order="locality")
+    assert plan.contributions == elemsN.shape[0] * 400
+    rowptr, colidx = plan.csr()
+    vals = plan.assemble(geo, code, omega, mu)
+    assert torch.equal(torch.view_as_real(vals), torch.view_as_real(plan.assemble(geo, code, omega, mu)))
+    A = CSRMatrix(rowptr, colidx, vals, plan.N)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
+    y = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
+    lhs = torch.dot(x, A.mult(y))  # torch.dot does not conjugate
+    rhs = torch.dot(y, A.mult(x))
+    assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
+    # Dirichlet: fused == separate, boundary rows are identity rows
+    bd_entity = np.zeros(plan.nEnt, dtype=np.uint8)
+    bd_entity[tab["bEdges"]] = 1
+    bd_entity[tab["nEdges"] + tab["bFaces"]] = 1
+    plan.set_dirichlet(bd_entity)
+    fused = plan.assemble(geo, code, omega, mu, apply_dirichlet=True)
+    perm = plan.dof_permutation().cpu().numpy().astype(np.int64)
+    bd_ref = np.concatenate([(tab["bEdges"][:, None] * 2 + np.arange(2)).reshape(-1),
+                             (tab["nEdges"] * 2 + tab["bFaces"][:, None] * 2 + np.arange(2)).reshape(-1)])
+    A.zeroRowsColumns(perm[bd_ref], 1.0)
+    assert torch.equal(torch.view_as_real(fused), torch.view_as_real(A.vals))
+    e = torch.zeros(plan.N, dtype=torch.complex128, device=vals.device)
+    e[torch.as_tensor(perm[bd_ref], device=vals.device)] = 1.0
+    Ae = CSRMatrix(rowptr, colidx, fused, plan.N).mult(e)
+    assert torch.equal(Ae, e)  # identity on the boundary block, zero coupling to the interior
+
+
+def test_spmv_and_vector_kernels_match_numpy():
+    from petgem_b200.device import CSRMatrix
+    from petgem_b200.krylov import VecKernels
+
+    g = golden("petsc_fixture_system.npz")
+    dev = torch.device("cuda")
+    A = CSRMatrix(torch.as_tensor(g["rowptr"], device=dev), torch.as_tensor(g["colidx"], device=dev),
+                  torch.as_tensor(g["vals"], device=dev), 4184)
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=4184) + 1j * rng.normal(size=4184)
+    import scipy.sparse as sp
+    As = sp.csr_matrix((g["vals"], g["colidx"], g["rowptr"]), shape=(4184, 4184))
+    y = A.mult(torch.as_tensor(x, device=dev)).cpu().numpy()
+    yr = As @ x
+    assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+    assert np.abs(A.diagonal().cpu().numpy() - As.diagonal()).max() == 0.0
+    # empty rows / tiny sizes
+    E = CSRMatrix(torch.zeros(4, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev),
+                  torch.zeros(0, dtype=torch.complex128, device=dev), 3)
+    assert torch.equal(E.mult(torch.ones(3, dtype=torch.complex128, device=dev)),
+                       torch.zeros(3, dtype=torch.complex128, device=dev))
+
+    n = 100003
+    vk = VecKernels(n, dev, kmax=32)
+    V = rng.normal(size=(31, n)) + 1j * rng.normal(size=(31, n))
+    w = rng.normal(size=n) + 1j * rng.normal(size=n)
+    Vd, wd = torch.as_tensor(V, device=dev), torch.as_tensor(w, device=dev)
+    out = torch.zeros(32, dtype=torch.complex128, device=dev)
+    for k in (1, 7, 8, 9, 31):
+        vk.mdot(k, Vd, n, wd, out)
+        ref = V[:k].conj() @ w
+        assert np.abs(out[:k].cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    vk.dot(Vd[3], wd, out)
+    assert abs(out[0].item() - np.vdot(V[3], w)) <= 1e-12 * abs(np.vdot(V[3], w))
+    vk.nrm2sq(wd, out)
+    assert abs(out[0].item().real - np.vdot(w, w).real) <= 1e-13 * np.vdot(w, w).real and out[0].item().imag == 0
+    alpha = rng.normal(size=31) + 1j * rng.normal(size=31)
+    ad = torch.as_tensor(alpha, device=dev)
+    for k in (1, 8, 20, 31):
+        w2 = wd.clone()
+        vk.maxpy(k, ad, -1.0, Vd, n, w2)
+        ref = w - alpha[:k] @ V[:k]
+        assert np.abs(w2.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    y2 = wd.clone()
+    vk.axpy(ad[:1], Vd[0], y2)
+    assert np.abs(y2.cpu().numpy() - (w + alpha[0] * V[0])).max() <= 1e-13 * np.abs(w).max()
+    y3 = wd.clone()
+    vk.aypx(ad[1:2], Vd[0], y3)
+    assert np.abs(y3.cpu().numpy() - (V[0] + alpha[1] * w)).max() <= 1e-13 * np.abs(w).max() * 4
+    y4 = torch.empty_like(wd)
+    vk.axpbypcz(ad[:1], Vd[0], ad[1:2], Vd[1], ad[2:3], wd, y4)
+    ref = alpha[0] * V[0] + alpha[1] * V[1] + alpha[2] * w
+    assert np.abs(y4.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    y5 = wd.clone()
+    vk.scal(ad[:1], y5)
+    assert np.abs(y5.cpu().numpy() - alpha[0] * w).max() <= 1e-13 * np.abs(w).max() * 4
+    # run-to-run determinism of the reductions
+    o1, o2 = torch.zeros(32, dtype=torch.complex128, device=dev), torch.zeros(32, dtype=torch.complex128, device=dev)
+    vk.mdot(31, Vd, n, wd, o1)
+    vk.mdot(31, Vd, n, wd, o2)
+    assert torch.equal(torch.view_as_real(o1), torch.view_as_real(o2))
+
+
+def _csem_system(topo, oracle, p):
+    """case1 physics on the reference test mesh: A (Dirichlet applied, fused) and b on the GPU."""
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, p)
+    nE = topo["edgesNodes"].shape[0]
+    bd_entity = np.zeros(plan.nEnt, dtype=np.uint8)
+    bd_entity[topo["bEdges"]] = 1
+    if p >= 2:
+        bd_entity[nE + topo["bFaces"]] = 1
+    plan.set_dirichlet(bd_entity)
+    vals = plan.assemble(geo, code, omega, mu, apply_dirichlet=True)
+    A = CSRMatrix(*plan.csr(), vals, plan.N)
+    dofs, *_ = oracle.compute_connectivity_dofs(topo["elemsE"].astype(np.int64), topo["elemsF"].astype(np.int64), p)
+    src = np.array([1750.0, 1750.0, -975.0])  # examples/case1 params.yaml:14
+    t = int(oracle.locate_points(topo["nodes"], topo["elemsN"], src[None, :])[0])
+    b = oracle.csem_rhs(plan.N, topo["nodes"][topo["elemsN"][t]], topo["elemsN"][t], topo["elemsE"][t],
+                        topo["edgesNodes"][topo["elemsE"][t]], topo["facesE"][topo["elemsF"][t]], dofs[t], p, src,
+                        0.0, 0.0, 1.0, 1.0, omega, mu)
+    b[topo["boundary_dofs_p%d" % p]] = 0.0  # solver.py:565-567
+    return A, b, dofs, omega, mu
+
+
+def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
+    """End of the path: GMRES(30)+Jacobi and BiCGStab+Jacobi on the GPU vs a direct solve of the
+    same system; receiver E-fields within 1e-6 relative (north_star)."""
+    import scipy.sparse.linalg as spla
+
+    from petgem_b200 import krylov
+
+    p = 1
+    A, b, dofs, omega, mu = _csem_system(topo, oracle, p)
+    As = A.to_scipy().tocsc()
+    xd = spla.spsolve(As, b)
+    bd = torch.as_tensor(b, device=A.vals.device)
+    rec = golden("case1_receivers.npy")
+    Ed = oracle.field_interpolator(xd, topo["nodes"], topo["elemsN"], topo["elemsE"], topo["edgesNodes"],
+                                   topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
+    scale = np.abs(Ed[:, :3]).max()
+    res = krylov.solve(A, bd, {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_max_it": 20000})
+    assert res.converged, (res.reason, res.iterations, res.residuals[-1])
+    x = res.x.cpu().numpy()
+    Eg = oracle.field_interpolator(x, topo["nodes"], topo["elemsN"], topo["elemsE"], topo["edgesNodes"],
+                                   topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
+    assert np.abs(Eg[:, :3] - Ed[:, :3]).max() <= 1e-6 * scale
+    # same iteration count as the oracle's GMRES restatement (same algorithm, same data)
+    dinv = 1.0 / As.diagonal()
+    xo, its_o, _ = oracle.gmres(lambda v: As @ v, b, rtol=1e-8, pc=lambda v: dinv * v)
+    res8 = krylov.solve(A, bd, {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-8})
+    assert res8.converged and abs(res8.iterations - its_o) <= max(3, its_o // 50), (res8.iterations, its_o)
+    resb = krylov.solve(A, bd, {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_max_it": 20000})
+    if resb.converged:  # BiCGStab may break down on this system; when it converges it must agree
+        Eb = oracle.field_interpolator(resb.x.cpu().numpy(), topo["nodes"], topo["elemsN"], topo["elemsE"],
+                                       topo["edgesNodes"], topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
+        assert np.abs(Eb[:, :3] - Ed[:, :3]).max() <= 1e-6 * scale
+
+
+def test_krylov_on_reference_petsc_fixture(oracle):
+    """The reference's tests/test_petsc.py system (matrix-A.dat, vector-b.dat)."""
+    import scipy.sparse.linalg as spla
+
+    from petgem_b200 import krylov
+    from petgem_b200.device import CSRMatrix
+
+    g = golden("petsc_fixture_system.npz")
+    dev = torch.device("cuda")
+    A = CSRMatrix(torch.as_tensor(g["rowptr"], device=dev), torch.as_tensor(g["colidx"], device=dev),
+                  torch.as_tensor(g["vals"], device=dev), 4184)
+    b = torch.as_tensor(g["b"], device=dev)
+    xd = spla.spsolve(A.to_scipy().tocsc(), g["b"])
+    res = krylov.solve(A, b, {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_gmres_restart": 100,
+                              "ksp_max_it": 4000})
+    assert res.converged
+    assert np.linalg.norm(res.x.cpu().numpy() - xd) <= 1e-6 * np.linalg.norm(xd)
+
+
+def test_bad_arguments_fail_loudly(topo):
+    from petgem_b200 import device as dv
+    from petgem_b200._lib import PetgemB200Error
+
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    from petgem_b200._lib import check, lib, ptr
+    rc = lib().pg_element_matrices(1, 7, ptr(geo), ptr(code), ptr(geo), ptr(geo), ptr(geo), None)
+    assert rc == -22 and b"order" in lib().pg_last_error()
+    with pytest.raises(PetgemB200Error):
+        check(rc, "pg_element_matrices")
+    with pytest.raises(PetgemB200Error):
+        dv.AssemblyPlan(el, 1, order=np.zeros(el.nEdges, dtype=np.int32))  # not a permutation

@@ -1,0 +1,143 @@
+"""CPU tests of the host-side product code (no GPU, no oracle in the product path):
+topology numbering, reference-element tables, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from petgem_b200 import basis, hvfem
+from petgem_b200 import mesh as pmesh
+
+
+def test_mesh_numbering_bit_exact(topo):
+    elemsN = topo["elemsN"].astype(np.int64)
+    T = elemsN.shape[0]
+    elemsE, edgesNodes = pmesh.computeEdges(elemsN, T)
+    elemsF, facesN = pmesh.computeFaces(elemsN, T)
+    assert np.array_equal(elemsE, topo["elemsE"]) and np.array_equal(edgesNodes, topo["edgesNodes"])
+    assert np.array_equal(elemsF, topo["elemsF"]) and np.array_equal(facesN, topo["facesN"])
+    facesE = pmesh.computeFacesEdges(elemsF, elemsE, facesN.shape[0], T)
+    assert np.array_equal(facesE, topo["facesE"])
+    bFacesN, bFaces, nb = pmesh.computeBoundaryFaces(elemsF, facesN)
+    assert nb == 2266 and np.array_equal(bFaces, topo["bFaces"])
+    bEdges = pmesh.computeBoundaryEdges(edgesNodes, bFacesN)
+    assert bEdges.size == 3399 and np.array_equal(bEdges, topo["bEdges"])
+    for p in (1, 2, 3):
+        dofs, de, df, dv, total = hvfem.computeConnectivityDOFS(elemsE, elemsF, p)
+        assert total == int(topo["total_dofs_p%d" % p])
+        assert np.array_equal(dofs[topo["dofs_sel"]], topo["dofs_rows_p%d" % p])
+        assert np.array_equal(dofs.sum(axis=0), topo["dofs_sum_p%d" % p])
+        _, bd = pmesh.computeBoundaries(dofs, de, df, bEdges, bFaces, p)
+        assert np.array_equal(bd, topo["boundary_dofs_p%d" % p])
+
+
+def test_mesh_rank_rows_fallback_matches_packed_keys():
+    rng = np.random.default_rng(3)
+    rows = np.sort(rng.integers(0, 50, size=(400, 3)), axis=1)
+    u1, inv1, f1 = pmesh._rank_rows(rows)
+    u2, f2, inv2 = np.unique(rows, axis=0, return_index=True, return_inverse=True)
+    assert np.array_equal(u1, u2) and np.array_equal(inv1, inv2.reshape(-1)) and np.array_equal(f1, f2)
+    big = rows.astype(np.int64) + (1 << 40)  # forces the lexicographic path
+    u3, inv3, _ = pmesh._rank_rows(big)
+    assert np.array_equal(u3 - (1 << 40), u2) and np.array_equal(inv3, inv1)
+
+
+def test_orientation_host_matches_reference(topo):
+    for t in range(0, 9453, 211):
+        eo, fo = hvfem.computeElementOrientation(topo["elemsE"][t], topo["elemsN"][t],
+                                                 topo["edgesNodes"][topo["elemsE"][t]], topo["facesE"][topo["elemsF"][t]])
+        assert np.array_equal(np.concatenate([eo, fo]), topo["orient"][t])
+        code = hvfem.pack_orientation(eo, fo)
+        eo2, fo2 = hvfem.unpack_orientation(code)
+        assert np.array_equal(eo, eo2) and np.array_equal(fo, fo2)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_basis_matches_reference_shape_functions(p):
+    g = golden("hvfem_shape.npz")
+    pts, eos, fos, ref = g["pts_%d" % p], g["eo_%d" % p], g["fo_%d" % p], g["shape_%d" % p]
+    N, C = basis.evaluate_expanded(p, pts)
+    for c in range(eos.shape[0]):
+        J, S = basis.local_to_expanded(p, eos[c], fos[c])
+        mine_n = np.moveaxis(N[J] * S[:, None, None], 0, -1)  # [pts, 3, n]
+        mine_c = np.moveaxis(C[J] * S[:, None, None], 0, -1)
+        assert np.abs(mine_n - ref[c, :, 0]).max() <= 1e-14 * max(1.0, np.abs(ref[c, :, 0]).max())
+        assert np.abs(mine_c - ref[c, :, 1]).max() <= 1e-14 * max(1.0, np.abs(ref[c, :, 1]).max())
+        n_, Sh, Cu = hvfem.shape3DETet(pts[0], np.ones(11, dtype=int) * p, eos[c], fos[c])
+        assert n_ == basis.ndof_element(p) and np.allclose(Sh, ref[c, 0, 0], atol=1e-13)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_tables_reproduce_reference_element_matrices(p):
+    """Host check of the contraction the kernels implement: Me = sum_c gM[c] SM[c][J,J] s s^T."""
+    g = golden("hvfem_elemental_p%d.npz" % p)
+    SM, SK = basis.element_tables(p)
+    worst = 0.0
+    for i in range(g["coords"].shape[0]):
+        X = g["coords"][i]
+        Jm = X[1:] - X[0]
+        gf = hvfem.geometric_factors(Jm, g["sigma"][i])
+        J, S = basis.local_to_expanded(p, g["eo"][i], g["fo"][i])
+        ss = np.outer(S, S)
+        Ke = np.einsum("c,cjk->jk", gf[:6], SK[:, J][:, :, J]) * ss
+        Me = np.einsum("c,cjk->jk", gf[6:], SM[:, J][:, :, J]) * ss
+        worst = max(worst, np.abs(Me - g["Me"][i]).max() / np.abs(g["Me"][i]).max(),
+                    np.abs(Ke - g["Ke"][i]).max() / np.abs(g["Ke"][i]).max())
+    assert worst < 1e-12, worst
+
+
+def test_tet_quadrature_exact():
+    from math import factorial as f
+    for deg in (3, 7, 13):
+        pts, w = basis.tet_quadrature(deg)
+        assert (w > 0).all() and abs(w.sum() - 1 / 6) < 1e-15
+        for a, b, c in ((deg, 0, 0), (1, deg - 2, 1), (deg // 3, deg // 3, deg - 2 * (deg // 3))):
+            exact = f(a) * f(b) * f(c) / f(a + b + c + 3)
+            assert abs((w * pts[:, 0] ** a * pts[:, 1] ** b * pts[:, 2] ** c).sum() - exact) <= 1e-13 * exact
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every symbol include/petgem_b200.h declares."""
+    from petgem_b200 import _lib
+
+    path = _lib.build()
+    handle = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "petgem_b200.h")).read()
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    assert L.pg_version() >= 100
+    for p, n in zip(range(1, 7), (6, 20, 45, 84, 140, 216)):
+        assert L.pg_ndof_element(p) == n == basis.ndof_element(p)
+        assert L.pg_nexp(p) == basis.expanded_layout(p)["nexp"]
+
+
+def test_synthetic_mesh_covers_all_orientation_codes():
+    from petgem_b200 import synthetic
+
+    nodes, elemsN = synthetic.kuhn_box(4)
+    assert elemsN.shape == (6 * 64, 4)
+    X = nodes[elemsN]
+    assert (np.linalg.det(X[:, 1:] - X[:, :1]) > 0).all()
+    tab = synthetic.mesh_tables(nodes, elemsN)
+    codes = set()
+    for t in range(elemsN.shape[0]):
+        eo, fo = hvfem.computeElementOrientation(tab["elemsE"][t], elemsN[t], tab["edgesNodes"][tab["elemsE"][t]],
+                                                 tab["facesE"][tab["elemsF"][t]])
+        codes |= set(fo.tolist())
+    assert codes == {0, 1, 2, 3, 4, 5}
+    sig = synthetic.layered_sigma(nodes, elemsN)
+    assert set(np.unique(sig[:, 0])) <= {3.3333, 1.0, 0.01}
+
+
+def test_petsc_options_parser():
+    from petgem_b200.krylov import parse_petsc_options
+
+    o = parse_petsc_options("# Solver options for PETSc\n-ksp_type gmres\n-pc_type sor\n-ksp_rtol 1e-8\n-ksp_monitor\n")
+    assert o == {"ksp_type": "gmres", "pc_type": "sor", "ksp_rtol": "1e-8", "ksp_monitor": True}
