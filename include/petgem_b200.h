@@ -166,6 +166,9 @@ int pg_zero_rows_columns(int64_t local_rows, int64_t row_begin, const int64_t *r
  * --------------------------------------------------------------------------- */
 int pg_spmv(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
             const double *x, double *y, void *stream);
+/* y = dscale .* (A x): MatMult fused with the PCJACOBI application (dscale = 1/diag, may be NULL) */
+int pg_spmv_scaled(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                   const double *x, const double *dscale, double *y, void *stream);
 /* diag [local_rows] complex128 of the owned block (for PCJACOBI) */
 int pg_csr_diagonal(int64_t local_rows, int64_t row_begin, const int64_t *rowptr, const int32_t *colidx,
                     const double *vals, double *diag, void *stream);
@@ -190,6 +193,11 @@ int pg_zmdotc(int64_t n, int k, const double *V, int64_t ldv, const double *w, d
 /* VecMAXPY: w += sum_i scale*alpha[i] V_i (alpha complex on device), one pass over w */
 int pg_zmaxpy(int64_t n, int k, const double *alpha, double scale, const double *V, int64_t ldv, double *w,
               void *stream);
+/* VecMAXPY followed by VecNorm of the result, fused: out[0] = sum |w_i|^2 after the update */
+int pg_zmaxpy_nrm2sq(int64_t n, int k, const double *alpha, double scale, const double *V, int64_t ldv, double *w,
+                     double *out, void *work, void *stream);
+/* y = alpha x, or y = x / Re(alpha) when inv_real != 0 (VecCopy + VecScale fused) */
+int pg_zcopy_scaled(int64_t n, const double *alpha, int inv_real, const double *x, double *y, void *stream);
 /* out[0] = sum |x_i|^2 (real, stored as complex with zero imaginary part) */
 int pg_dznrm2sq(int64_t n, const double *x, double *out, void *work, void *stream);
 int64_t pg_reduce_workspace_bytes(int kmax);

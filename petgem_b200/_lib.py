@@ -80,6 +80,7 @@ SIGNATURES = {
     "pg_assemble": (C.c_int, [_p, _p, _p, _p, _d, _i32, _d, _p, _p]),
     "pg_zero_rows_columns": (C.c_int, [_i64, _i64, _p, _p, _p, _d, _p, _p]),
     "pg_spmv": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
+    "pg_spmv_scaled": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "pg_csr_diagonal": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p]),
     "pg_zaxpy": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_zaypx": (C.c_int, [_i64, _p, _p, _p, _p]),
@@ -89,6 +90,8 @@ SIGNATURES = {
     "pg_zdotc": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "pg_zmdotc": (C.c_int, [_i64, _i32, _p, _i64, _p, _p, _p, _p]),
     "pg_zmaxpy": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p]),
+    "pg_zmaxpy_nrm2sq": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p, _p, _p]),
+    "pg_zcopy_scaled": (C.c_int, [_i64, _p, _i32, _p, _p, _p]),
     "pg_dznrm2sq": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_reduce_workspace_bytes": (_i64, [_i32]),
 }

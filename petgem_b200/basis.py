@@ -339,3 +339,18 @@ def element_tables(p: int):
             S[c] = T[a, a] if a == b else T[a, b] + T[b, a]
         out.append(np.ascontiguousarray(S))
     return out[0], out[1]
+
+
+# denominators that make the reference tensors integral (exact rationals: integrals of
+# integer-coefficient polynomials over the master tetrahedron); used by the p <= 2 kernel,
+# which keeps SK*DK and SM*DM as 16-bit integers in shared memory (pg_assemble.cu)
+INTEGER_SCALES = {1: (6, 120), 2: (120, 5040), 3: (5040, 362880)}
+
+
+def integer_tables(p: int):
+    """(SM*DM, SK*DK) rounded to integers, with the worst rounding distance (must be ~1e-12)."""
+    DK, DM = INTEGER_SCALES[p]
+    SM, SK = element_tables(p)
+    nM, nK = np.rint(SM * DM), np.rint(SK * DK)
+    err = max(np.abs(SM * DM - nM).max(), np.abs(SK * DK - nK).max())
+    return nM.astype(np.int64), nK.astype(np.int64), float(err)

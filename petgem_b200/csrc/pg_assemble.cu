@@ -12,6 +12,8 @@
 // with the 12-term geometric contraction, adds them at precomputed positions, and
 // streams the finished rows to HBM with coalesced 16-byte stores.  Ae is never
 // materialised, nothing is atomically updated, the result is bit-reproducible.
+#include <cuda_pipeline.h>
+
 #include "pg_plan.cuh"
 
 namespace pg {
@@ -26,6 +28,7 @@ struct AsmArgs {
     const int32_t *selfpos;
     const int64_t *valoff;
     const uint8_t *bd_entity;  // null: no Dirichlet
+    const EntHdr *hdr;         // owned entities in processing order
     const double *geo;
     const uint32_t *code;
     const double *table;
@@ -120,6 +123,410 @@ __global__ void __launch_bounds__(THREADS) assemble_kernel(const AsmArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// p = 1, 2: shared-memory integer-table kernel
+//
+// * For p <= 2 every row entity has the same number of rows R (1 or 2) and the
+//   orientation-resolved function set collapses: at p = 2 the two functions of a face are,
+//   for each of the six face orientations, two of the three functions
+//   psi0 = l_c w_ab, psi1 = l_a w_bc, psi2 = l_b w_ca up to sign (w_xy = l_x grad l_y -
+//   l_y grad l_x): 12 edge + 4 x 3 face = 24 functions (kFaceLut2).
+// * The reference tensors are integrals of integer-coefficient polynomials over the master
+//   tetrahedron, i.e. exact rationals: SK * DK and SM * DM are small integers (p=1: DK=6,
+//   DM=120; p=2: DK=120, DM=5040, |n| <= 252; asserted on the host in basis.py and in
+//   tests/test_host.py).  They are kept in shared memory as biased 16-bit integers, 32 bytes
+//   per (row function, column) entry instead of 96, and widened to fp64 exactly with the
+//   2^52 trick (one DADD); the 1/D and -omega*mu factors ride on the final sign multiply.
+// * Columns are addressed by their LOCAL index k (orientation independent) and the face
+//   variant selects a plane, so the 8 lanes of a group always hit 8 different 16-byte bank
+//   groups: conflict-free table reads.
+// * Eight lanes own one entity: R*n = 40 (6 at p = 1) entries per incident element, 5 per
+//   lane over 3 distinct columns.  The element that first touches a column stores, later
+//   ones read-modify-write (firstmask), so the tile is never zero-filled.
+// ---------------------------------------------------------------------------
+template <int P>
+struct Small {
+    static constexpr int R = P;                      // rows per entity (edges p, faces p(p-1): 1 / 2)
+    static constexpr int n = Ord<P>::n;              // 6 / 20
+    static constexpr int NX = (P == 1) ? 6 : 24;     // reduced function set
+    static constexpr int NENT = (P == 1) ? 36 : 960; // table entries (plane 0: 24x24, planes 1,2: 24x8)
+    static constexpr int G = 8;
+    static constexpr int NCOL = (P == 1) ? 1 : 3;    // distinct columns per lane
+    static constexpr int IPL = (P == 1) ? 1 : 5;     // items per lane
+    static constexpr int MC = 8;                     // records staged per chunk
+    static constexpr double DK = (P == 1) ? 6.0 : 120.0;
+    static constexpr double DM = (P == 1) ? 120.0 : 5040.0;
+    // 16-bit code = 0x3000 | ((n + BIAS) << SHIFT): fraction (n + BIAS) 2^(SHIFT-12), bias at 1/2
+    static constexpr int BIAS = (P == 1) ? 16 : 256;   // |n| <= 8 (p=1), <= 252 (p=2)
+    static constexpr int SHIFT = (P == 1) ? 7 : 3;
+    static constexpr double UNIT = (P == 1) ? 7.105427357601002e-15 : 1.1368683772161603e-13;  // 2^-47 / 2^-43
+};
+
+// (orientation o, family d) -> base function 0..2 and sign bit, 3 bits each
+constexpr uint64_t kFaceLut2 =
+    (0ull << 0) | (1ull << 3) | (1ull << 6) | (2ull << 9) | (2ull << 12) | (0ull << 15) | (6ull << 18) |
+    (5ull << 21) | (4ull << 24) | (6ull << 27) | (5ull << 30) | (4ull << 33);
+
+// general expanded index of reduced function jr (used once, to fill the shared table)
+template <int P>
+__device__ __forceinline__ int expanded_of_reduced(int jr) {
+    if (P == 1 || jr < 12) return jr;
+    const int f = (jr - 12) / 3, b = (jr - 12) % 3;
+    const int o = (b == 2) ? 1 : 0, fam = (b == 0) ? 0 : 1;
+    return 12 + (f * 6 + o) * 2 + fam;
+}
+
+// reduced index of a ROW function (slot, d) under orientation code; neg = sign flip
+template <int P>
+__device__ __forceinline__ int reduced_row(int slot, int d, uint32_t code, unsigned &neg) {
+    if (P == 1 || slot < 6) {
+        neg = (((code >> slot) & 1u) && ((d & 1) == 0)) ? 1u : 0u;
+        return slot * P + d;
+    }
+    const int f = slot - 6;
+    const unsigned o = (code >> (6 + 3 * f)) & 7u;
+    const unsigned e = (unsigned)(kFaceLut2 >> (6 * o + 3 * d)) & 7u;
+    neg = e >> 2;
+    return 12 + f * 3 + (int)(e & 3u);
+}
+
+struct ColDesc {     // one local column k handled by this lane: fixed for the whole kernel
+    int k, slot, d;
+    int recoff;      // byte offset of slotpos[slot] in an IncRecord
+    unsigned ebit;   // edge column: orientation bit that flips the sign (0 if none)
+    int fshift;      // face column: shift of its 3-bit orientation code, -1 for edge columns
+};
+
+// Table codes.  An integer numerator n in [-256, 255] is stored as the 16-bit code
+// 0x3000 | ((n + 256) << 3); dropped into bits 8..23 of the high word 0x43000000 (one PRMT) it
+// forms, with a zero low word, the double X = 2^52 (1 + (n+256)/512) = Xb + n 2^43, Xb = 1.5 2^52.
+// The contraction sum_c g_c X_c is taken as is and the constant part sum_c g_c Xb (same operation
+// order, so all-zero entries cancel bit-exactly) is subtracted once; 2^-43 rides on the final scale.
+// Rounding: <= 3 ulp of 2^52 sum|g| against entries of size 2^43 |n| sum|g| -> ~2e-15 norm-relative.
+__device__ __forceinline__ double code_lo(unsigned w, unsigned hi_const) {
+    return __hiloint2double((int)__byte_perm(w, hi_const, 0x7104), 0);
+}
+__device__ __forceinline__ double code_hi(unsigned w, unsigned hi_const) {
+    return __hiloint2double((int)__byte_perm(w, hi_const, 0x7324), 0);
+}
+
+template <int P>
+struct SmallCtx {  // per-lane state of assemble_small_kernel that process_element needs
+    const uint4 *tabA;
+    const uint2 *tabB;
+    double2 *buf;
+    ColDesc col[Small<P>::NCOL];
+    double invK, invM;
+    unsigned hi_const;
+    int row4, L;
+    bool lane_valid, use_bd;
+};
+
+// one incident element: the lane's (up to) 5 entries of the local rows, added into the tile
+template <int P>
+__device__ __forceinline__ void process_element(const SmallCtx<P> &cx, const double2 (&g)[6], uint32_t cd,
+                                                const IncRecord *recp) {
+    using S = Small<P>;
+    const unsigned char *rbytes = reinterpret_cast<const unsigned char *>(recp);
+    const unsigned w24 = *reinterpret_cast<const unsigned *>(rbytes + 24);  // slotpos[10] | slot<<16
+    const unsigned w28 = *reinterpret_cast<const unsigned *>(rbytes + 28);  // bdmask | firstmask<<16
+    const int rslot = (w24 >> 16) & 0xff;
+    const unsigned bdm = cx.use_bd ? (w28 & 0xffffu) : 0u;
+    const unsigned fm = w28 >> 16;
+
+    int jrow[S::R];
+    unsigned jneg[S::R];
+#pragma unroll
+    for (int d = 0; d < S::R; ++d) jrow[d] = reduced_row<P>(rslot, d, cd, jneg[d]);
+
+    // constant part of the contraction (all codes at the bias), same operation order as below
+    const double xb = __hiloint2double(0x43380000, 0);
+    double cK = g[0].x * xb;
+    cK = fma(g[0].y, xb, cK);
+    cK = fma(g[1].x, xb, cK);
+    cK = fma(g[1].y, xb, cK);
+    cK = fma(g[2].x, xb, cK);
+    cK = fma(g[2].y, xb, cK);
+    double cM = g[3].x * xb;
+    cM = fma(g[3].y, xb, cM);
+    cM = fma(g[4].x, xb, cM);
+    cM = fma(g[4].y, xb, cM);
+    cM = fma(g[5].x, xb, cM);
+    cM = fma(g[5].y, xb, cM);
+
+    int cent[S::NCOL], cmul[S::NCOL], cpos[S::NCOL];
+    unsigned cneg[S::NCOL], cfirst[S::NCOL], cbd[S::NCOL];
+#pragma unroll
+    for (int j = 0; j < S::NCOL; ++j) {
+        const ColDesc &cj = cx.col[j];
+        cneg[j] = (cd & cj.ebit) ? 1u : 0u;
+        cent[j] = cj.k;
+        cmul[j] = (P == 1) ? 6 : 24;
+        if (P >= 2 && cj.fshift >= 0) {
+            const unsigned o = (cd >> cj.fshift) & 7u;
+            const unsigned e = (unsigned)(kFaceLut2 >> (6 * o + 3 * cj.d)) & 7u;
+            const int b = (int)(e & 3u);
+            cneg[j] = e >> 2;
+            if (b) {  // face variant planes: 8 wide, column (k - 8) & 7 keeps the bank phase k mod 8
+                cent[j] = 576 + (b - 1) * 192 + ((cj.k - 8) & 7);
+                cmul[j] = 8;
+            }
+        }
+        cpos[j] = *reinterpret_cast<const uint16_t *>(rbytes + cj.recoff) + cj.d;
+        cfirst[j] = (fm >> cj.slot) & 1u;
+        cbd[j] = (bdm >> cj.slot) & 1u;
+    }
+#pragma unroll
+    for (int q = 0; q < S::IPL; ++q) {
+        const int j = (P == 1) ? 0 : (q < 2 ? 0 : (q < 4 ? 1 : 2));
+        const int row = (P == 1) ? 0 : (q == 4 ? cx.row4 : (q & 1));
+        const int jr = (S::R == 1) ? jrow[0] : (row ? jrow[S::R - 1] : jrow[0]);
+        const unsigned neg = cneg[j] ^ ((S::R == 1) ? jneg[0] : (row ? jneg[S::R - 1] : jneg[0]));
+        const int ent = cent[j] + jr * cmul[j];
+        const uint4 w0 = cx.tabA[ent];
+        const uint2 w1 = cx.tabB[ent];
+        const unsigned hc = cx.hi_const;
+        double kk = g[0].x * code_lo(w0.x, hc);
+        kk = fma(g[0].y, code_hi(w0.x, hc), kk);
+        kk = fma(g[1].x, code_lo(w0.y, hc), kk);
+        kk = fma(g[1].y, code_hi(w0.y, hc), kk);
+        kk = fma(g[2].x, code_lo(w0.z, hc), kk);
+        kk = fma(g[2].y, code_hi(w0.z, hc), kk);
+        double mm = g[3].x * code_lo(w0.w, hc);
+        mm = fma(g[3].y, code_hi(w0.w, hc), mm);
+        mm = fma(g[4].x, code_lo(w1.x, hc), mm);
+        mm = fma(g[4].y, code_hi(w1.x, hc), mm);
+        mm = fma(g[5].x, code_lo(w1.y, hc), mm);
+        mm = fma(g[5].y, code_hi(w1.y, hc), mm);
+        kk -= cK;
+        mm -= cM;
+        // +-2^-43/D (orientation signs), 0 for a Dirichlet column
+        double sK = neg ? -cx.invK : cx.invK, sM = neg ? -cx.invM : cx.invM;
+        if (cbd[j]) {
+            sK = 0.0;
+            sM = 0.0;
+        }
+        if (P == 1 && !cx.lane_valid) continue;
+        double2 *dst = cx.buf + cpos[j] + row * cx.L;
+        double2 cur = make_double2(0.0, 0.0);
+        if (!cfirst[j]) cur = *dst;
+        cur.x = fma(sK, kk, cur.x);
+        cur.y = fma(sM, mm, cur.y);
+        *dst = cur;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void load_geo(const AsmArgs &a, int64_t t, double2 (&g)[6], uint32_t &cd) {
+    const double2 *gp = reinterpret_cast<const double2 *>(a.geo + t * 12);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g[q] = __ldg(gp + q);
+    cd = __ldg(a.code + t);
+}
+
+template <int P>
+__global__ void __launch_bounds__(512, 1) assemble_small_kernel(const AsmArgs a) {
+    using S = Small<P>;
+    constexpr int G = S::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: integer table, SoA: A [NENT] x 16 B (K0..K5, M0, M1) | B [NENT] x 8 B (M2..M5) |
+    //         staged records [groups][MC+1] (the +1 staggers the groups over the banks) |
+    //         tiles [groups][R*L] complex
+    uint4 *s_tabA = reinterpret_cast<uint4 *>(smem_raw);
+    uint2 *s_tabB = reinterpret_cast<uint2 *>(s_tabA + S::NENT);
+    const int groups = blockDim.x / G;
+    IncRecord *s_rec = reinterpret_cast<IncRecord *>(s_tabB + S::NENT);
+    EntHdr *s_hdr = reinterpret_cast<EntHdr *>(s_rec + groups * 2 * (S::MC + 1));  // 3 headers per group
+    double2 *s_buf = reinterpret_cast<double2 *>(s_hdr + groups * 3);
+
+    {   // fill the integer table from the general fp64 table (L2 resident)
+        unsigned short *tA = reinterpret_cast<unsigned short *>(s_tabA);
+        unsigned short *tB = reinterpret_cast<unsigned short *>(s_tabB);
+        for (int i = threadIdx.x; i < S::NENT * 12; i += blockDim.x) {
+            const int e = i / 12, c = i - e * 12;
+            int jr, kr;
+            bool valid = true;
+            if (P == 1) {
+                jr = e / 6;
+                kr = e - jr * 6;
+            } else if (e < 576) {
+                jr = e / 24;
+                const int k = e - jr * 24;
+                valid = valid && k < 20;
+                kr = (k < 12) ? k : 12 + 3 * ((k - 12) >> 1);
+            } else {
+                const int e2 = e - 576, b = 1 + e2 / 192, r2 = e2 % 192;
+                jr = r2 >> 3;
+                const int k = 12 + (((r2 & 7) + 4) & 7);  // inverse of (k - 8) & 7 on k = 12..19
+                kr = 12 + 3 * ((k - 12) >> 1) + b;
+            }
+            int nint = 0;
+            if (valid) {
+                const double v = __ldg(a.table + ((int64_t)expanded_of_reduced<P>(jr) * Ord<P>::nexp +
+                                                  expanded_of_reduced<P>(kr)) * 12 + c);
+                nint = (int)rint(v * (c < 6 ? S::DK : S::DM));
+            }
+            const unsigned short u = (unsigned short)(0x3000 | ((nint + S::BIAS) << S::SHIFT));
+            if (c < 8) tA[e * 8 + c] = u; else tB[e * 4 + (c - 8)] = u;
+        }
+    }
+    __syncthreads();
+
+    const int grp = threadIdx.x / G;
+    const int lane = threadIdx.x % G;
+    const unsigned mask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
+    IncRecord *rec = s_rec + grp * 2 * (S::MC + 1);  // two staging buffers (double buffered)
+
+    SmallCtx<P> cx;
+    cx.tabA = s_tabA;
+    cx.tabB = s_tabB;
+    cx.buf = s_buf + (size_t)grp * a.bufstride;
+#pragma unroll
+    for (int j = 0; j < S::NCOL; ++j) {
+        int k = (j == 0) ? lane : (j == 1) ? lane + 8 : 16 + (lane & 3);
+        if (k >= S::n) k = S::n - 1;  // p=1: lanes 6,7 are idle (lane_valid)
+        cx.col[j].k = k;
+        slot_of_local<P>(k, cx.col[j].slot, cx.col[j].d);
+        cx.col[j].recoff = 4 + 2 * cx.col[j].slot;
+        const bool face = cx.col[j].slot >= 6;
+        cx.col[j].ebit = (!face && (cx.col[j].d & 1) == 0) ? (1u << cx.col[j].slot) : 0u;
+        cx.col[j].fshift = face ? 6 + 3 * (cx.col[j].slot - 6) : -1;
+    }
+    cx.lane_valid = lane < S::n;
+    cx.row4 = lane >> 2;
+    cx.invK = (1.0 / S::DK) * S::UNIT;           // 2^-(52 - 12 + SHIFT) / DK
+    cx.invM = (a.mass_scale / S::DM) * S::UNIT;  // ... * (-omega mu) / DM
+    cx.hi_const = 0x43000000u;
+    cx.use_bd = a.bd_entity != nullptr;
+
+    // Software pipeline over the group's entities e_0, e_1, ... (stride ngroups), all prefetches
+    // by cp.async straight into shared memory (no registers held across the element loop):
+    //   while e_k is processed, the header of e_{k+2} and the records of e_{k+1} are in flight,
+    //   and the geometric factors of e_{k+1}'s first element are fetched before e_k's rows are
+    //   streamed out.
+    const int64_t nb = a.b1 - a.b0;
+    const int64_t ngroups = (int64_t)gridDim.x * groups;
+    int64_t i = blockIdx.x * (int64_t)groups + grp;
+    EntHdr *hring = s_hdr + grp * 3;  // headers of e_k, e_{k+1}, e_{k+2} at slots k%3, (k+1)%3, (k+2)%3
+    int hs = 0;                       // ring slot of the current entity
+    int cur = 0;                      // staging buffer of the current entity's records
+    double2 gA[6], gB[6];
+    uint32_t cA = 0, cB = 0;
+
+    // prologue: headers of e_0, e_1; records and first geometry of e_0
+    if (lane < 2) {
+        if (i < nb) __pipeline_memcpy_async(reinterpret_cast<char *>(hring) + 16 * lane,
+                                            reinterpret_cast<const char *>(a.hdr + i) + 16 * lane, 16);
+        if (i + ngroups < nb)
+            __pipeline_memcpy_async(reinterpret_cast<char *>(hring + 1) + 16 * lane,
+                                    reinterpret_cast<const char *>(a.hdr + i + ngroups) + 16 * lane, 16);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncwarp(mask);
+    if (i < nb && !(cx.use_bd && hring[0].bd)) {
+        if (lane < min((int)S::MC, (int)hring[0].m)) {
+            const char *src = reinterpret_cast<const char *>(a.rec + hring[0].inc0 + lane);
+            __pipeline_memcpy_async(rec + lane, src, 16);
+            __pipeline_memcpy_async(reinterpret_cast<char *>(rec + lane) + 16, src + 16, 16);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncwarp(mask);
+        load_geo<P>(a, rec[0].elem, gA, cA);
+    }
+    for (; i < nb; i += ngroups) {
+        const EntHdr *hc = hring + hs;
+        const int hs1 = (hs == 2) ? 0 : hs + 1, hs2 = (hs1 == 2) ? 0 : hs1 + 1;
+        const EntHdr *hn = hring + hs1;
+        const int m = hc->m, L = hc->L;
+        const bool bd = cx.use_bd && hc->bd;
+        double2 *out = a.vals + hc->valoff;
+        cx.L = L;
+        // prefetch: records of e_{k+1} (its header arrived during e_{k-1}), header of e_{k+2}
+        const bool next_ok = (i + ngroups < nb) && !(cx.use_bd && hn->bd);
+        IncRecord *rnext = rec + (cur ^ 1) * (S::MC + 1);
+        if (next_ok && lane < min((int)S::MC, (int)hn->m)) {
+            const char *src = reinterpret_cast<const char *>(a.rec + hn->inc0 + lane);
+            __pipeline_memcpy_async(rnext + lane, src, 16);
+            __pipeline_memcpy_async(reinterpret_cast<char *>(rnext + lane) + 16, src + 16, 16);
+        }
+        if (lane < 2 && i + 2 * ngroups < nb)
+            __pipeline_memcpy_async(reinterpret_cast<char *>(hring + hs2) + 16 * lane,
+                                    reinterpret_cast<const char *>(a.hdr + i + 2 * ngroups) + 16 * lane, 16);
+        __pipeline_commit();
+
+        if (bd) {
+            const int sp = hc->selfpos;
+            for (int it = lane; it < S::R * L; it += G) {
+                const int d = it / L, c = it - d * L;
+                __stcs(out + it, make_double2(c == sp + d ? a.diag : 0.0, 0.0));
+            }
+        } else {
+            IncRecord *rc = rec + cur * (S::MC + 1);
+            for (int c0 = 0; c0 < m; c0 += S::MC) {
+                const int mc = min(S::MC, m - c0);
+                if (c0 > 0) {  // rare: more than MC incident elements, fetch the next chunk synchronously
+                    __syncwarp(mask);
+                    if (lane < mc) {
+                        const int4 *src = reinterpret_cast<const int4 *>(a.rec + hc->inc0 + c0 + lane);
+                        int4 *dst = reinterpret_cast<int4 *>(rc + lane);
+                        dst[0] = __ldg(src);
+                        dst[1] = __ldg(src + 1);
+                    }
+                    __syncwarp(mask);
+                    load_geo<P>(a, rc[0].elem, gA, cA);
+                }
+                for (int ia = 0; ia < mc; ia += 2) {
+                    const bool has_b = ia + 1 < mc;
+                    if (has_b) load_geo<P>(a, rc[ia + 1].elem, gB, cB);
+                    process_element<P>(cx, gA, cA, rc + ia);
+                    __syncwarp(mask);  // the next element may touch the same positions from other lanes
+                    if (has_b) {
+                        if (ia + 2 < mc) load_geo<P>(a, rc[ia + 2].elem, gA, cA);
+                        process_element<P>(cx, gB, cB, rc + ia + 1);
+                        __syncwarp(mask);
+                    }
+                }
+            }
+        }
+        // everything prefetched at the top has landed long ago
+        __pipeline_wait_prior(0);
+        __syncwarp(mask);
+        if (next_ok) load_geo<P>(a, rnext[0].elem, gA, cA);
+        if (!bd) {
+            for (int it = lane; it < S::R * L; it += G) __stcs(out + it, cx.buf[it]);
+            __syncwarp(mask);  // tile reusable
+        }
+        hs = hs1;
+        cur ^= 1;
+    }
+}
+
+template <int P>
+static int launch_assemble_small(const pg_plan *pl, AsmArgs a, cudaStream_t st) {
+    using S = Small<P>;
+    const int L = pl->max_rowlen;
+    const size_t table_bytes = (size_t)S::NENT * 24;
+    const size_t per_group = 2 * (S::MC + 1) * sizeof(IncRecord) + 3 * sizeof(EntHdr) + (size_t)S::R * L * 16;
+    const size_t budget = 227 * 1024 - 1024;
+    PG_REQUIRE(table_bytes + 4 * per_group <= budget, PG_ERANGE,
+               "pg_assemble: row length %d does not fit in shared memory", L);
+    int groups = (int)std::min<size_t>(64, (budget - table_bytes) / per_group);
+    groups -= groups % 4;  // whole warps
+    const int threads = groups * S::G;
+    a.rc = S::R;
+    a.bufstride = S::R * L;
+    const size_t smem = table_bytes + (size_t)groups * per_group;
+    auto kern = assemble_small_kernel<P>;
+    PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nb = pl->b1 - pl->b0;
+    const int64_t grid = std::min<int64_t>((nb + groups - 1) / groups, (int64_t)kNumSMs);
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
 template <int P, int G, int THREADS>
 static int launch_assemble(const pg_plan *pl, AsmArgs a, cudaStream_t st) {
     constexpr int GROUPS = THREADS / G;
@@ -166,6 +573,7 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
     a.b0 = pl->b0, a.b1 = pl->b1;
     a.ent_order = pl->ent_order, a.row_base = pl->row_base, a.inc_ptr = pl->inc_ptr, a.rec = pl->rec;
     a.rowlen = pl->rowlen, a.selfpos = pl->selfpos, a.valoff = pl->valoff;
+    a.hdr = pl->hdr;
     a.bd_entity = apply_dirichlet ? pl->bd_entity : nullptr;
     a.geo = geo, a.code = code, a.table = table;
     a.mass_scale = mass_scale, a.diag = diag;
@@ -173,8 +581,8 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
     a.rc = 1, a.bufstride = 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pl->p) {
-        case 1: return launch_assemble<1, 8, 256>(pl, a, st);
-        case 2: return launch_assemble<2, 32, 256>(pl, a, st);
+        case 1: return launch_assemble_small<1>(pl, a, st);
+        case 2: return launch_assemble_small<2>(pl, a, st);
         case 3: return launch_assemble<3, 32, 128>(pl, a, st);
         case 4: return launch_assemble<4, 32, 128>(pl, a, st);
         case 5: return launch_assemble<5, 32, 128>(pl, a, st);

@@ -33,10 +33,11 @@ __device__ __forceinline__ unsigned group_mask() {
 // SpMV: G lanes per row, coalesced (colidx, vals) streams, x gathered through L2
 // ---------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t *__restrict__ rowptr,
-                                                   const int32_t *__restrict__ colidx,
-                                                   const double2 *__restrict__ vals, const double2 *__restrict__ x,
-                                                   double2 *__restrict__ y) {
+__global__ void __launch_bounds__(256, 6) spmv_kernel(int64_t rows, const int64_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      const double2 *__restrict__ vals,
+                                                      const double2 *__restrict__ x,
+                                                      const double2 *__restrict__ dscale, double2 *__restrict__ y) {
     const int lane = threadIdx.x % G;
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
     const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -45,14 +46,19 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t *
         const int64_t a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
         double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
         int64_t j = a + lane;
-        for (; j + G < b; j += 2 * G) {
+        // 4 independent (index, value, x) streams per lane: the kernel is latency bound otherwise
+        for (; j + 3 * G < b; j += 4 * G) {
             const int32_t c0 = __ldg(colidx + j), c1 = __ldg(colidx + j + G);
+            const int32_t c2 = __ldg(colidx + j + 2 * G), c3 = __ldg(colidx + j + 3 * G);
             const double2 v0 = __ldcs(vals + j), v1 = __ldcs(vals + j + G);
-            const double2 x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+            const double2 v2 = __ldcs(vals + j + 2 * G), v3 = __ldcs(vals + j + 3 * G);
+            const double2 x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
             cfma(acc0, v0, x0);
             cfma(acc1, v1, x1);
+            cfma(acc0, v2, x2);
+            cfma(acc1, v3, x3);
         }
-        if (j < b) {
+        for (; j < b; j += G) {
             const int32_t c0 = __ldg(colidx + j);
             cfma(acc0, __ldcs(vals + j), __ldg(x + c0));
         }
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t *
             acc0.x += __shfl_down_sync(gm, acc0.x, o, G);
             acc0.y += __shfl_down_sync(gm, acc0.y, o, G);
         }
-        if (lane == 0) y[row] = acc0;
+        if (lane == 0) y[row] = dscale ? cmul(__ldg(dscale + row), acc0) : acc0;
     }
 }
 
@@ -246,11 +252,13 @@ __global__ void __launch_bounds__(kRedThreads) reduce_stage2(const double2 *__re
     }
 }
 
-// w += scale * sum_i alpha[i] V_i, one pass over w per chunk of K vectors
-template <int K>
-__global__ void __launch_bounds__(256) maxpy_kernel(int64_t n, int kcount, const double2 *__restrict__ alpha,
-                                                    double scale, const double2 *__restrict__ V, int64_t ldv,
-                                                    double2 *__restrict__ w) {
+// w += scale * sum_i alpha[i] V_i, one pass over w per chunk of K vectors; NORM: also the partial
+// sums of |w|^2 of the updated vector (the VecNorm that follows VecMAXPY in GMRES, fused)
+template <int K, bool NORM>
+__global__ void __launch_bounds__(kRedThreads) maxpy_kernel(int64_t n, int kcount, const double2 *__restrict__ alpha,
+                                                            double scale, const double2 *__restrict__ V,
+                                                            int64_t ldv, double2 *__restrict__ w,
+                                                            double2 *__restrict__ partial) {
     double2 al[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -258,13 +266,28 @@ __global__ void __launch_bounds__(256) maxpy_kernel(int64_t n, int kcount, const
         al[i].x *= scale;
         al[i].y *= scale;
     }
+    double2 nrm[1] = {make_double2(0.0, 0.0)};
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         double2 v = w[j];
 #pragma unroll
         for (int i = 0; i < K; ++i)
             if (i < kcount) cfma(v, al[i], V[i * ldv + j]);
         w[j] = v;
+        if (NORM) {
+            nrm[0].x = fma(v.x, v.x, nrm[0].x);
+            nrm[0].x = fma(v.y, v.y, nrm[0].x);
+        }
     }
+    if (NORM) block_reduce_store<1>(nrm, 1, partial, kRedBlocks);
+}
+
+// y = alpha x, or y = x / Re(alpha) (VecCopy + VecScale of the GMRES normalisation, fused)
+__global__ void __launch_bounds__(256) zcopy_scaled_kernel(int64_t n, const double2 *__restrict__ alpha, int inv_real,
+                                                           const double2 *__restrict__ x, double2 *__restrict__ y) {
+    double2 al = *alpha;
+    if (inv_real) al = make_double2(1.0 / al.x, 0.0);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = cmul(al, x[i]);
 }
 
 static inline unsigned ew_grid(int64_t n) {
@@ -283,15 +306,20 @@ extern "C" {
 
 int pg_spmv(int64_t rows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
             double *y, void *stream) {
+    return pg_spmv_scaled(rows, rowptr, colidx, vals, x, nullptr, y, stream);
+}
+
+int pg_spmv_scaled(int64_t rows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
+                   const double *dscale, double *y, void *stream) {
     PG_REQUIRE(rows >= 0, PG_EINVAL, "pg_spmv: rows < 0");
     if (rows == 0) return PG_OK;
     PG_REQUIRE(rowptr && x && y, PG_EINVAL, "pg_spmv: null pointer");  // colidx/vals may be null when nnz == 0
     cudaStream_t st = (cudaStream_t)stream;
     // lanes per row from the mean row length (host knows it only through the caller: use 16,
     // the best trade-off for the 15..120 nnz/row of p=1..2; long rows are still coalesced)
-    constexpr int G = 16;
-    int64_t blocks = std::min<int64_t>((rows * G + 255) / 256, (int64_t)kNumSMs * 64);
-    spmv_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), D2(y));
+    constexpr int G = 8;
+    int64_t blocks = std::min<int64_t>((rows * G + 255) / 256, (int64_t)kNumSMs * 96);
+    spmv_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y));
     PG_LAUNCH_OK();
     return PG_OK;
 }
@@ -403,10 +431,38 @@ int pg_zmaxpy(int64_t n, int k, const double *alpha, double scale, const double 
     cudaStream_t st = (cudaStream_t)stream;
     for (int c0 = 0; c0 < k; c0 += kDotChunk) {
         const int kc = std::min(kDotChunk, k - c0);
-        maxpy_kernel<kDotChunk><<<ew_grid(n), 256, 0, st>>>(n, kc, CD2(alpha) + c0, scale,
-                                                           CD2(V) + (int64_t)c0 * ldv, ldv, D2(w));
+        maxpy_kernel<kDotChunk, false><<<ew_grid(n), kRedThreads, 0, st>>>(
+            n, kc, CD2(alpha) + c0, scale, CD2(V) + (int64_t)c0 * ldv, ldv, D2(w), nullptr);
         PG_LAUNCH_OK();
     }
+    return PG_OK;
+}
+
+int pg_zmaxpy_nrm2sq(int64_t n, int k, const double *alpha, double scale, const double *V, int64_t ldv, double *w,
+                     double *out, void *work, void *stream) {
+    PG_REQUIRE(n >= 0 && k >= 1, PG_EINVAL, "pg_zmaxpy_nrm2sq: bad size");
+    PG_REQUIRE(alpha && V && w && out && work, PG_EINVAL, "pg_zmaxpy_nrm2sq: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < k; c0 += kDotChunk) {
+        const int kc = std::min(kDotChunk, k - c0);
+        if (c0 + kDotChunk < k)
+            maxpy_kernel<kDotChunk, false><<<ew_grid(n), kRedThreads, 0, st>>>(
+                n, kc, CD2(alpha) + c0, scale, CD2(V) + (int64_t)c0 * ldv, ldv, D2(w), nullptr);
+        else  // last pass: fixed reduction grid so that the result is reproducible
+            maxpy_kernel<kDotChunk, true><<<kRedBlocks, kRedThreads, 0, st>>>(
+                n, kc, CD2(alpha) + c0, scale, CD2(V) + (int64_t)c0 * ldv, ldv, D2(w), D2(work));
+        PG_LAUNCH_OK();
+    }
+    reduce_stage2<<<1, kRedThreads, 0, st>>>(D2(work), D2(out));
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int pg_zcopy_scaled(int64_t n, const double *alpha, int inv_real, const double *x, double *y, void *stream) {
+    if (n == 0) return PG_OK;
+    PG_REQUIRE(n > 0 && alpha && x && y, PG_EINVAL, "pg_zcopy_scaled: bad argument");
+    zcopy_scaled_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(n, CD2(alpha), inv_real, CD2(x), D2(y));
+    PG_LAUNCH_OK();
     return PG_OK;
 }
 

@@ -147,9 +147,13 @@ __global__ void __launch_bounds__(kSymWarps * 32)
                 r.slot = (uint8_t)(v - r.elem * nslots);
                 r.pad0 = 0;
                 r.bdmask = 0;
-                r.pad1 = 0;
+                uint16_t fm = 0;
 #pragma unroll
-                for (int s = 0; s < PG_SLOTS; ++s) r.slotpos[s] = (s < nslots) ? pos[rank[a * nslots + s]] : 0;
+                for (int s = 0; s < PG_SLOTS; ++s) {
+                    r.slotpos[s] = (s < nslots) ? pos[rank[a * nslots + s]] : 0;
+                    if (s < nslots && first[a * nslots + s]) fm |= (uint16_t)(1u << s);
+                }
+                r.firstmask = fm;
                 rec[i0 + a] = r;
             }
         }
@@ -254,6 +258,43 @@ __global__ void set_bdmask_kernel(int64_t nInc, int nslots, const int32_t *__res
     rec[i].bdmask = m;
 }
 
+constexpr int kProcWindow = 16384;  // entities per window of the processing order
+
+__global__ void hdr_keys_kernel(int64_t b0, int64_t nb, const int32_t *__restrict__ ent_order,
+                                const int32_t *__restrict__ inc_ptr, const uint8_t *__restrict__ bd_entity,
+                                int32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int32_t g = ent_order[b0 + i];
+    int m = inc_ptr[g + 1] - inc_ptr[g];
+    if (m > 255) m = 255;
+    if (bd_entity && bd_entity[g]) m = 0;
+    keys[i] = (int32_t)(((i / kProcWindow) << 8) | m);
+    vals[i] = (int32_t)i;
+}
+
+__global__ void hdr_fill_kernel(int64_t b0, int64_t nb, const int32_t *__restrict__ order,
+                                const int32_t *__restrict__ ent_order, const int64_t *__restrict__ row_base,
+                                const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ rowlen,
+                                const int32_t *__restrict__ selfpos, const int64_t *__restrict__ valoff,
+                                const uint8_t *__restrict__ bd_entity, EntHdr *__restrict__ hdr) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t bl = order[i];
+    const int32_t g = ent_order[b0 + bl];
+    EntHdr h;
+    h.valoff = valoff[bl];
+    h.inc0 = inc_ptr[g];
+    h.ent = g;
+    h.m = (uint16_t)(inc_ptr[g + 1] - inc_ptr[g]);
+    h.L = (uint16_t)rowlen[g];
+    h.selfpos = (uint16_t)selfpos[g];
+    h.bd = (bd_entity && bd_entity[g]) ? 1 : 0;
+    h.rows = (uint8_t)(row_base[b0 + bl + 1] - row_base[b0 + bl]);
+    h.pad[0] = h.pad[1] = 0;
+    hdr[i] = h;
+}
+
 static int bits_for(int64_t n) {
     int b = 1;
     while ((1LL << b) < n) ++b;
@@ -295,6 +336,34 @@ static int build_incidence(int64_t T, int p, const int32_t *elemsE, const int32_
     return PG_OK;
 }
 
+// headers of the owned entities in processing order (rebuilt when the Dirichlet set changes)
+static int build_headers(pg_plan *pl, cudaStream_t st) {
+    const int64_t nb = pl->b1 - pl->b0;
+    if (nb <= 0) return PG_OK;
+    if (!pl->hdr) PG_CUDA_OK(cudaMalloc((void **)&pl->hdr, nb * sizeof(EntHdr)));
+    DevBuf keys, vals, keys_out, order, tmp;
+    PG_CUDA_OK(cudaMalloc(&keys.p, nb * 4));
+    PG_CUDA_OK(cudaMalloc(&vals.p, nb * 4));
+    PG_CUDA_OK(cudaMalloc(&keys_out.p, nb * 4));
+    PG_CUDA_OK(cudaMalloc(&order.p, nb * 4));
+    const unsigned grid = (unsigned)((nb + 255) / 256);
+    hdr_keys_kernel<<<grid, 256, 0, st>>>(pl->b0, nb, pl->ent_order, pl->inc_ptr, pl->bd_entity,
+                                          keys.as<int32_t>(), vals.as<int32_t>());
+    PG_LAUNCH_OK();
+    const int bits = 8 + bits_for(nb / kProcWindow + 2);
+    size_t bytes = 0;
+    PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.as<int32_t>(), keys_out.as<int32_t>(),
+                                               vals.as<int32_t>(), order.as<int32_t>(), nb, 0, bits, st));
+    PG_CUDA_OK(cudaMalloc(&tmp.p, bytes));
+    PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.as<int32_t>(), keys_out.as<int32_t>(),
+                                               vals.as<int32_t>(), order.as<int32_t>(), nb, 0, bits, st));
+    hdr_fill_kernel<<<grid, 256, 0, st>>>(pl->b0, nb, order.as<int32_t>(), pl->ent_order, pl->row_base, pl->inc_ptr,
+                                          pl->rowlen, pl->selfpos, pl->valoff, pl->bd_entity, pl->hdr);
+    PG_LAUNCH_OK();
+    PG_CUDA_OK(cudaStreamSynchronize(st));
+    return PG_OK;
+}
+
 static int check_sizes(int64_t T, int p, int64_t nE, int64_t nF, int64_t &nEnt, int64_t &N) {
     PG_REQUIRE(p >= 1 && p <= PG_MAX_ORDER, PG_EINVAL, "polynomial order %d outside 1..%d", p, PG_MAX_ORDER);
     PG_REQUIRE(T > 0 && nE > 0 && nF > 0, PG_EINVAL, "plan: empty mesh (T=%lld nE=%lld nF=%lld)", (long long)T,
@@ -324,6 +393,7 @@ void pg_plan_destroy(pg_plan *pl) {
     cudaFree(pl->rowlen);
     cudaFree(pl->selfpos);
     cudaFree(pl->valoff);
+    cudaFree(pl->hdr);
     cudaFree(pl->bd_entity);
     delete pl;
 }
@@ -506,6 +576,8 @@ int pg_plan_create(int64_t T, int p, const int32_t *elemsE, const int32_t *elems
         PG_CUDA_OK(cudaStreamSynchronize(st));
     }
     PG_CUDA_OK(cudaStreamSynchronize(st));
+    rc = build_headers(pl, st);
+    if (rc) return rc;
     guard.p = nullptr;
     *out = pl;
     return PG_OK;
@@ -564,7 +636,7 @@ extern "C" int pg_plan_set_dirichlet(pg_plan *pl, const int32_t *elemsE, const i
     if (!bd_entity) {
         cudaFree(pl->bd_entity);
         pl->bd_entity = nullptr;
-        return PG_OK;
+        return build_headers(pl, st);
     }
     PG_REQUIRE(elemsE && elemsF, PG_EINVAL, "pg_plan_set_dirichlet: null connectivity");
     if (!pl->bd_entity) PG_CUDA_OK(cudaMalloc((void **)&pl->bd_entity, pl->nEnt));
@@ -572,5 +644,5 @@ extern "C" int pg_plan_set_dirichlet(pg_plan *pl, const int32_t *elemsE, const i
     set_bdmask_kernel<<<(unsigned)((pl->nInc + 255) / 256), 256, 0, st>>>(pl->nInc, pl->nslots, elemsE, elemsF,
                                                                          pl->nE, pl->nF, pl->bd_entity, pl->rec);
     PG_LAUNCH_OK();
-    return PG_OK;
+    return build_headers(pl, st);
 }

@@ -12,9 +12,25 @@ struct __align__(16) IncRecord {
     uint8_t slot;                // which slot of t this entity is
     uint8_t pad0;
     uint16_t bdmask;             // bit s' set: slot s' of t is a Dirichlet entity
-    uint16_t pad1;
+    uint16_t firstmask;          // bit s' set: this element is the first contributor to the dofs of slot s'
 };
 static_assert(sizeof(IncRecord) == 32, "IncRecord must be 32 bytes");
+
+// One header per owned entity, stored in PROCESSING order: entities of a window are
+// visited grouped by their number of incident elements so that the sub-warp groups of
+// a warp run the same trip counts (storage order of the CSR rows is unaffected).
+struct __align__(16) EntHdr {
+    int64_t valoff;    // offset of the entity's first row in vals
+    int32_t inc0;      // first incidence record
+    int32_t ent;       // global entity id
+    uint16_t m;        // incident elements
+    uint16_t L;        // row length
+    uint16_t selfpos;  // position of the entity's own dofs in its column list
+    uint8_t bd;        // Dirichlet entity
+    uint8_t rows;      // rows of the entity
+    int32_t pad[2];
+};
+static_assert(sizeof(EntHdr) == 32, "EntHdr must be 32 bytes");
 
 }  // namespace pg
 
@@ -38,6 +54,7 @@ struct pg_plan {
     // owned block range and value offsets
     int64_t b0 = 0, b1 = 0, row_begin = 0, row_end = 0;
     int64_t *valoff = nullptr;      // [b1-b0+1] offset into vals of the first row of owned block
+    pg::EntHdr *hdr = nullptr;      // [b1-b0] headers in processing order
     int64_t nnz = 0, contributions = 0;
     int max_rowlen = 0;
     uint8_t *bd_entity = nullptr;   // [nEnt] own copy, set by pg_plan_set_dirichlet

@@ -239,12 +239,14 @@ class CSRMatrix:
         self.rows = int(rowptr.numel() - 1)
         self.nnz = int(vals.numel())
 
-    def mult(self, x: torch.Tensor, y: torch.Tensor = None) -> torch.Tensor:
-        """y = A x  (MatMult); x has N entries, y the owned rows."""
+    def mult(self, x: torch.Tensor, y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:
+        """y = A x  (MatMult); x has N entries, y the owned rows.  With row_scale, y = row_scale .* (A x)
+        (the Jacobi preconditioner applied in the SpMV epilogue)."""
         if y is None:
             y = torch.empty((self.rows,), dtype=torch.complex128, device=x.device)
         check(
-            lib().pg_spmv(self.rows, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x), ptr(y), stream_ptr()),
+            lib().pg_spmv_scaled(self.rows, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x),
+                                 ptr(row_scale), ptr(y), stream_ptr()),
             "pg_spmv",
         )
         return y

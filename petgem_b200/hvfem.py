@@ -36,8 +36,8 @@ def dofs_of_elements(elemsE_rows, elemsF_rows, elem_ids, nEdges, nFaces, Nord):
     eF = np.asarray(elemsF_rows, dtype=np.int64).reshape(-1, 4)
     t = np.asarray(elem_ids, dtype=np.int64).reshape(-1)
     ne, nf, nv = basis.ndof_edge(Nord), basis.ndof_face(Nord), basis.ndof_volume(Nord)
-    parts = [(eE[:, :, None] * ne + np.arange(ne)).reshape(-1, 6 * ne),
-             (nEdges * ne + eF[:, :, None] * nf + np.arange(nf)).reshape(-1, 4 * nf),
+    parts = [(eE[:, :, None] * ne + np.arange(ne)).reshape(eE.shape[0], 6 * ne),
+             (nEdges * ne + eF[:, :, None] * nf + np.arange(nf)).reshape(eF.shape[0], 4 * nf),
              nEdges * ne + nFaces * nf + t[:, None] * nv + np.arange(nv)[None, :]]
     return np.concatenate(parts, axis=1)
 

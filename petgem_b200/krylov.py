@@ -75,12 +75,12 @@ class Operator:
             self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin)
         self.spmv_calls = 0
 
-    def matvec(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
         if self.ctx is not None and self.ctx.world > 1:
             self.ctx.gather(x, self.send, self.full)
-            self.A_halo.mult(self.full, y)
+            self.A_halo.mult(self.full, y, row_scale)
         else:
-            self.A.mult(x, y)
+            self.A.mult(x, y, row_scale)
         self.spmv_calls += 1
         return y
 
@@ -92,10 +92,9 @@ class Operator:
             check(lib().pg_zpointwise_mult(self.n, ptr(x), ptr(self.inv_diag), ptr(y), stream_ptr()), "pg_zpointwise_mult")
         return y
 
-    def apply(self, x, y, tmp):
-        """y = M^-1 (A x)."""
-        self.matvec(x, tmp)
-        return self.precond(tmp, y)
+    def apply(self, x, y, tmp=None):
+        """y = M^-1 (A x); the Jacobi scaling rides in the SpMV epilogue."""
+        return self.matvec(x, y, self.inv_diag)
 
 
 class VecKernels:
@@ -127,6 +126,18 @@ class VecKernels:
 
     def maxpy(self, k, alpha, scale, V, ldv, w):
         check(lib().pg_zmaxpy(self.n, k, ptr(alpha), float(scale), ptr(V), ldv, ptr(w), stream_ptr()), "pg_zmaxpy")
+
+    def maxpy_nrm2sq(self, k, alpha, scale, V, ldv, w, out):
+        """w += scale * sum alpha_i V_i and out[0] = ||w||^2 of the result, one pass."""
+        check(lib().pg_zmaxpy_nrm2sq(self.n, k, ptr(alpha), float(scale), ptr(V), ldv, ptr(w), ptr(out),
+                                     ptr(self.work), stream_ptr()), "pg_zmaxpy_nrm2sq")
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.allreduce(out[:1])
+        return out
+
+    def copy_scaled(self, alpha, x, y, inv_real=False):
+        check(lib().pg_zcopy_scaled(self.n, ptr(alpha), 1 if inv_real else 0, ptr(x), ptr(y), stream_ptr()),
+              "pg_zcopy_scaled")
 
     def axpy(self, alpha, x, y):
         check(lib().pg_zaxpy(self.n, ptr(alpha), ptr(x), ptr(y), stream_ptr()), "pg_zaxpy")
@@ -195,13 +206,11 @@ def gmres(op: Operator, b: torch.Tensor, rtol=1e-8, restart=30, maxit=10000, ato
         sn = np.zeros(restart, dtype=np.complex128)
         k = 0
         while k < restart and its < maxit:
-            op.apply(V[k], w, tmp)                     # w = M^-1 A v_k
+            op.apply(V[k], w, tmp)                     # w = M^-1 A v_k   (MatMult + PCApply fused)
             vk.mdot(k + 1, V, n, w, hcol)              # h_0..k = V^H w   (VecMDot)
-            vk.maxpy(k + 1, hcol, -1.0, V, n, w)       # w -= sum h_i v_i (VecMAXPY)
-            vk.nrm2sq(w, hcol[k + 1:k + 2])
+            vk.maxpy_nrm2sq(k + 1, hcol, -1.0, V, n, w, hcol[k + 1:k + 2])  # w -= sum h_i v_i, ||w||^2
             hcol[k + 1] = torch.sqrt(hcol[k + 1].real)
-            V[k + 1].copy_(w)
-            vk.scal(hcol[k + 1:k + 2], V[k + 1], inv_real=True)
+            vk.copy_scaled(hcol[k + 1:k + 2], w, V[k + 1], inv_real=True)   # v_{k+1} = w / ||w||
             h = hcol[: k + 2].cpu().numpy()            # the one host sync of the iteration
             for i in range(k):                         # previous Givens rotations
                 t = cs[i] * h[i] + sn[i] * h[i + 1]
@@ -288,6 +297,51 @@ def bicgstab(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, 
     return SolveResult(x, maxit, hist, False, "maxit")
 
 
+def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None):
+    """Conjugate-orthogonal CG for the complex SYMMETRIC system (KSPCG with -ksp_cg_type symmetric):
+    one SpMV, two unconjugated dots and three vector updates per iteration, no restart.  Jacobi enters
+    symmetrically through z = D^-1 r; convergence is tested on the preconditioned residual like PETSc."""
+    n, dev = op.n, b.device
+    vk = VecKernels(n, dev, op.ctx, kmax=4)
+    z_ = lambda: torch.zeros((n,), dtype=_C128, device=dev)  # noqa: E731
+    x, r, z, p_, q = z_(), b.clone(), z_(), z_(), z_()
+    sc = torch.zeros((8,), dtype=_C128, device=dev)
+    one = torch.ones((1,), dtype=_C128, device=dev)
+
+    def udot(u, v):  # unconjugated u^T v = conj(conj(u))^T v
+        return complex(vk.dot(torch.conj_physical(u), v, sc)[0].item())
+
+    op.precond(r, z)
+    bnorm = math.sqrt(vk.nrm2sq(z, sc)[0].real.item())
+    if bnorm == 0.0:
+        return SolveResult(x, 0, [0.0], True, "zero rhs")
+    tol = max(rtol * bnorm, atol)
+    p_.copy_(z)
+    rho = udot(r, z)
+    hist = [bnorm]
+    for it in range(1, maxit + 1):
+        op.matvec(p_, q)
+        den = udot(p_, q)
+        if den == 0.0 or rho == 0.0:
+            return SolveResult(x, it - 1, hist, False, "breakdown")
+        alpha = rho / den
+        sc[1], sc[2] = alpha, -alpha
+        vk.axpy(sc[1:2], p_, x)
+        vk.axpy(sc[2:3], q, r)
+        op.precond(r, z)
+        res = math.sqrt(vk.nrm2sq(z, sc)[0].real.item())
+        hist.append(res)
+        if monitor:
+            monitor(it, res)
+        if res <= tol:
+            return SolveResult(x, it, hist, True, "rtol")
+        rho_new = udot(r, z)
+        sc[1] = rho_new / rho
+        vk.aypx(sc[1:2], z, p_)  # p = z + beta p
+        rho = rho_new
+    return SolveResult(x, maxit, hist, False, "maxit")
+
+
 def parse_petsc_options(path_or_text):
     """Read the PETSc options file passed on the PETGEM command line
     (kernel.py:15, examples/case1/petsc.opts) -> dict of the options we honour."""
@@ -320,4 +374,8 @@ def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, 
         return gmres(op, b, rtol=rtol, restart=int(o.get("ksp_gmres_restart", 30)), maxit=maxit, monitor=monitor)
     if ksp in ("bcgs", "bicgstab"):
         return bicgstab(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
-    raise ValueError("unsupported ksp_type %r (gmres, bcgs)" % ksp)
+    if ksp == "cg":
+        if str(o.get("ksp_cg_type", "symmetric")) != "symmetric":
+            raise ValueError("A is complex symmetric, not Hermitian: use -ksp_cg_type symmetric")
+        return cocg(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
+    raise ValueError("unsupported ksp_type %r (gmres, bcgs, cg)" % ksp)

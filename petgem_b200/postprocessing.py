@@ -1,0 +1,76 @@
+"""Thin stand-in for ``petgem/postprocessing.py``: receiver fields from ``x{i}.dat``.
+
+``fieldInterpolator`` follows postprocessing.py:479-616 (locate receivers, evaluate the basis at
+the receiver, E = sum_j x_j N_j, H = sum_j x_j curl N_j / (i omega mu)), vectorised with the
+product's basis tables; output is ``<directory>/fields.npz`` (+ ``.h5`` when h5py exists)
+instead of the reference's HDF5/VTK writers (out of scope).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import hvfem
+from .common import Print, Timers
+from .parallel import MPIEnvironment, readPetscVector
+from .preprocessing import locate_points, read_receivers
+
+
+def fieldInterpolator(solution_vector, nodes, elemsN, elemsE, edgesN, elemsF, facesE, dof_connectivity, points,
+                      inputSetup):
+    """postprocessing.py:479-616 -> fields [nPoints, 6] complex (Ex,Ey,Ez,Hx,Hy,Hz)."""
+    model, run = inputSetup.model, inputSetup.run
+    p = run.get('nord')
+    mode = model.get('mode')
+    data_model = model.get(mode)
+    frequency = data_model.get('source').get('frequency') if mode == 'csem' else data_model.get('frequency')
+    omega, mu = frequency * 2. * np.pi, 4. * np.pi * 1e-7
+    Const = 1j * omega * mu
+    x = np.asarray(solution_vector.getArray() if hasattr(solution_vector, 'getArray') else solution_vector)
+    points = np.atleast_2d(points)
+    idx = locate_points(nodes, elemsN, points)
+    lost = np.nonzero(idx < 0)[0]
+    if lost.size:
+        Print.master('        The following receivers were not located and will not be taken into account ' + str(lost))
+        points, idx = points[idx >= 0], idx[idx >= 0]
+        if idx.size == 0:
+            Print.master('     No point has been found. Nothing to do. Aborting')
+            exit(-1)
+    fields = np.zeros((points.shape[0], 6), dtype=np.complex128)
+    for i, (pt, t) in enumerate(zip(points, idx)):
+        coordEle = nodes[elemsN[t]]
+        jac, ijac = hvfem.computeJacobian(coordEle)
+        eo, fo = hvfem.computeElementOrientation(elemsE[t], elemsN[t], edgesN[elemsE[t]], facesE[elemsF[t]])
+        X = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, pt)
+        basis, curl = hvfem.computeBasisFunctions(eo, fo, jac, ijac, p, X)
+        xe = x[dof_connectivity[t]]
+        fields[i, :3] = basis[:, :, 0] @ xe
+        fields[i, 3:] = (curl[:, :, 0] @ xe) / Const
+    return fields
+
+
+class Postprocessing():
+    """Class for postprocessing."""
+
+    def __init__(self):
+        return
+
+    def run(self, inputSetup):
+        Timers()["Postprocessing"].start()
+        if MPIEnvironment().rank == 0:
+            out_dir = inputSetup.output.get('directory_scratch')
+            tab = np.load(out_dir + '/mesh_tables.npz')
+            receivers = read_receivers(inputSetup.model.get('receivers'))
+            out = {}
+            for i in range(inputSetup.run.get('num_polarizations')):
+                x = readPetscVector(out_dir + '/x%d.dat' % i)
+                out['fields_%d' % i] = fieldInterpolator(x, tab['nodes'], tab['elemsN'], tab['elemsE'], tab['edgesNodes'],
+                                                         tab['elemsF'], tab['facesE'], tab['dofs'], receivers, inputSetup)
+            out['receiver_coordinates'] = receivers
+            out['run_time_s'] = Timers().elapsed('Assembly') + Timers().elapsed('Solver')
+            np.savez(inputSetup.output.get('directory') + '/fields.npz', **out)
+            self.fields = out
+        Timers()["Postprocessing"].stop()
+
+
+def unitary_test():
+    """Unitary test for postprocessing.py script."""

@@ -1,0 +1,168 @@
+"""Thin, vectorised stand-in for ``petgem/preprocessing.py`` (rank-0 serial stage).
+
+Produces exactly the scratch files ``Solver.setup`` reads, in PETSc
+binary format, from a Gmsh 2.2 ASCII mesh -- without meshio/h5py/petsc4py (absent here).
+Topology and numbering come from ``petgem_b200.mesh`` / ``hvfem`` (bit-identical to the
+reference).  MT boundary-element tables (preprocessing.py:314-381) are not produced:
+outside the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import hvfem
+from . import mesh as pmesh
+from .common import Print, Timers
+from .parallel import (MPIEnvironment, createSequentialDenseMatrixWithArray, createSequentialVectorWithArray,
+                       writeParallelDenseMatrix, writePetscVector)
+
+
+def read_gmsh22(path):
+    """Gmsh 2.2 ASCII, tetrahedra only -> (points [Nn,3], tets [T,4] 0-based, physical tag [T])."""
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    try:
+        i = lines.index("$Nodes")
+        nn = int(lines[i + 1])
+        pts = np.array([ln.split()[1:4] for ln in lines[i + 2:i + 2 + nn]], dtype=np.float64)
+        i = lines.index("$Elements")
+        ne = int(lines[i + 1])
+    except ValueError:
+        Print.master("     %s is not a Gmsh 2.2 ASCII mesh" % path)
+        exit(-1)
+    tets, tags = [], []
+    for ln in lines[i + 2:i + 2 + ne]:
+        f = ln.split()
+        if len(f) > 2 and f[1] == "4":
+            ntags = int(f[2])
+            tags.append(int(f[3]))
+            tets.append(f[3 + ntags:3 + ntags + 4])
+    return pts, np.array(tets, dtype=np.int64) - 1, np.array(tags, dtype=np.int64)
+
+
+def read_receivers(path):
+    """Receiver positions: .npy / text, or the contiguous 'data' dataset of PETGEM's .h5 files
+    (h5py when available, else the raw layout of the shipped files: float64 rows at offset 2048)."""
+    if path.endswith(".npy"):
+        return np.load(path)
+    if path.endswith(".h5"):
+        try:
+            import h5py
+
+            with h5py.File(path, "r") as fh:
+                return fh["data"][()]
+        except ImportError:
+            raw = np.fromfile(path, dtype=np.uint8)
+            return raw[2048:2048 + ((raw.size - 2048) // 24) * 24].view("<f8").reshape(-1, 3)
+    return np.loadtxt(path).reshape(-1, 3)
+
+
+def locate_points(nodes, elemsN, points, tol=1.0e-12):
+    """Containing element of each point (lowest index), -1 if none: vectorised stand-in for
+    Delaunay.find_simplex with the mesh connectivity (preprocessing.py:414-420)."""
+    points = np.atleast_2d(points)
+    X0 = nodes[elemsN[:, 0]]
+    Jt = np.stack([nodes[elemsN[:, k]] - X0 for k in (1, 2, 3)], axis=2)
+    lo, hi = nodes[elemsN].min(axis=1), nodes[elemsN].max(axis=1)
+    out = np.full(points.shape[0], -1, dtype=np.int64)
+    for i, pt in enumerate(points):
+        cand = np.nonzero(((pt >= lo - 1e-9) & (pt <= hi + 1e-9)).all(axis=1))[0]
+        if cand.size == 0:
+            continue
+        loc = np.linalg.solve(Jt[cand], np.broadcast_to(pt - X0[cand], (cand.size, 3))[..., None])[..., 0]
+        ok = (loc >= -tol).all(axis=1) & (1.0 - loc.sum(axis=1) >= -tol)
+        if ok.any():
+            out[i] = cand[np.argmax(ok)]
+    return out
+
+
+class Preprocessing():
+    """Class for preprocessing."""
+
+    def __init__(self):
+        return
+
+    def run(self, inputSetup):
+        Timers()["Preprocessing"].start()
+        parEnv = MPIEnvironment()
+        if parEnv.rank == 0:
+            self._run_master(inputSetup)
+        try:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.barrier()
+        except Exception:
+            pass
+        Timers()["Preprocessing"].stop()
+
+    def _run_master(self, inputSetup):
+        model, run, output = inputSetup.model, inputSetup.run, inputSetup.output
+        out_dir = output.get('directory_scratch')
+        p = run.get('nord')
+        mode = model.get('mode')
+        data_model = model.get(mode)
+        points, cells, tags = read_gmsh22(model.get('mesh'))
+        nElems = cells.shape[0]
+
+        def dump(name, arr):
+            arr = np.asarray(arr, dtype=np.float64).reshape(nElems, -1)
+            writeParallelDenseMatrix(out_dir + '/' + name,
+                                     createSequentialDenseMatrixWithArray(arr.shape[0], arr.shape[1], arr))
+
+        Print.master('     Nodal coordinates')
+        dump('nodes.dat', points[cells])
+        Print.master('     Mesh connectivity')
+        dump('meshConnectivity.dat', cells)
+        Print.master('     Edges connectivity')
+        elemsE, edgesNodes = pmesh.computeEdges(cells, nElems)
+        dump('edges.dat', elemsE)
+        dump('edgesNodes.dat', edgesNodes[elemsE])
+        Print.master('     Faces connectivity')
+        elemsF, facesN = pmesh.computeFaces(cells, nElems)
+        nFaces = facesN.shape[0]
+        dump('faces.dat', elemsF)
+        Print.master('     Faces-edges connectivity')
+        facesE = pmesh.computeFacesEdges(elemsF, elemsE, nFaces, nElems)
+        dump('facesEdges.dat', facesE[elemsF])
+        Print.master('     DOFs connectivity')
+        dofs, dof_edges, dof_faces, _, total_num_dofs = hvfem.computeConnectivityDOFS(elemsE, elemsF, p)
+        dump('dofs.dat', dofs)
+        Print.master('     Conductivity model')
+        i_model = data_model.get('sigma')
+        if run.get('conductivity_from_file'):
+            sig_file = i_model.get('file')
+            conductivityModel = np.load(sig_file) if sig_file.endswith('.npy') else read_receivers(sig_file)[:, :2]
+        else:
+            elemsS = tags - 1
+            conductivityModel = np.stack([np.asarray(i_model.get('horizontal'), dtype=np.float64)[elemsS],
+                                          np.asarray(i_model.get('vertical'), dtype=np.float64)[elemsS]], axis=1)
+        dump('conductivityModel.dat', conductivityModel)
+        Print.master('     Boundaries')
+        bFacesN, bFaces, nbFaces = pmesh.computeBoundaryFaces(elemsF, facesN)
+        if mode == 'csem':
+            bEdges = pmesh.computeBoundaryEdges(edgesNodes, bFacesN)
+            _, bd = pmesh.computeBoundaries(dofs, dof_edges, dof_faces, bEdges, bFaces, p)
+            writePetscVector(out_dir + '/boundaries.dat', createSequentialVectorWithArray(bd.astype(np.float64)))
+            src = np.asarray(data_model.get('source').get('position'), dtype=np.float64)
+            srcElem = int(locate_points(points, cells, src)[0])
+            if srcElem < 0:
+                Print.master('        Source no located in the computational domain. Please, verify source position or improve the mesh quality.')
+                exit(-1)
+            data_source = np.concatenate([cells[srcElem], points[cells[srcElem]].reshape(-1), elemsF[srcElem],
+                                          facesE[elemsF[srcElem]].reshape(-1), elemsE[srcElem],
+                                          edgesNodes[elemsE[srcElem]].reshape(-1), dofs[srcElem]]).astype(np.float64)
+            writePetscVector(out_dir + '/source.dat', createSequentialVectorWithArray(data_source))
+        else:
+            Print.master('     MT boundary elements (preprocessing.py:314-381) are not produced by petgem_b200')
+        valence = np.array([50, 200, 400, 800, 1400, 2500])  # preprocessing.py:470-473
+        writePetscVector(out_dir + '/nnz.dat',
+                         createSequentialVectorWithArray(np.full(total_num_dofs, valence[p - 1], dtype=np.float64)))
+        # tables the post-processing needs (the reference recomputes them from the mesh)
+        np.savez(out_dir + '/mesh_tables.npz', nodes=points, elemsN=cells, elemsE=elemsE, edgesNodes=edgesNodes,
+                 elemsF=elemsF, facesE=facesE, dofs=dofs)
+        Print.master('     Number of elements: %d, dofs: %d' % (nElems, total_num_dofs))
+
+
+def unitary_test():
+    """Unitary test for preprocessing.py script."""

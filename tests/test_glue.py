@@ -1,0 +1,178 @@
+"""Drop-in surface around the hot path: params file, PETSc-binary scratch files, preprocessing
+(CPU), and the kernel.py command line end to end (GPU)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def write_msh22(path, nodes, elemsN, tags):
+    with open(path, "w") as fh:
+        fh.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % nodes.shape[0])
+        for i, (x, y, z) in enumerate(nodes):
+            fh.write("%d %.17g %.17g %.17g\n" % (i + 1, x, y, z))
+        fh.write("$EndNodes\n$Elements\n%d\n" % elemsN.shape[0])
+        for i, (t, tag) in enumerate(zip(elemsN, tags)):
+            fh.write("%d 4 2 %d %d %d %d %d %d\n" % (i + 1, tag, tag, t[0] + 1, t[1] + 1, t[2] + 1, t[3] + 1))
+        fh.write("$EndElements\n")
+
+
+PARAMS = """
+model:
+  mode: csem
+  csem:
+    sigma:
+      horizontal: [1., 0.01, 1., 3.3333]
+      vertical: [1., 0.01, 1., 3.3333]
+    source:
+      frequency: 2.
+      position: [1750., 1750., -975.]
+      azimuth: 0.
+      dip: 0.
+      current: 1.
+      length: 1.
+  mesh: %(mesh)s
+  receivers: %(rec)s
+run:
+  nord: %(nord)d
+  cuda: True
+output:
+  vtk: False
+  directory: %(out)s
+  directory_scratch: %(tmp)s
+"""
+
+
+def make_case(tmp_path, topo, nord=1):
+    mesh = str(tmp_path / "case.msh")
+    write_msh22(mesh, topo["nodes"], topo["elemsN"], topo["tags"])
+    rec = str(tmp_path / "receivers.npy")
+    np.save(rec, golden("case1_receivers.npy"))
+    params = str(tmp_path / "params.yaml")
+    with open(params, "w") as fh:
+        fh.write(PARAMS % dict(mesh=mesh, rec=rec, nord=nord, out=str(tmp_path / "out"), tmp=str(tmp_path / "tmp")))
+    opts = str(tmp_path / "petsc.opts")
+    with open(opts, "w") as fh:
+        fh.write("# Solver options for PETSc\n-ksp_type gmres\n-pc_type sor\n-ksp_rtol 1e-11\n-ksp_max_it 30000\n")
+    return params, opts
+
+
+def test_input_parameters_schema(tmp_path, topo):
+    from petgem_b200.common import InputParameters
+
+    params, _ = make_case(tmp_path, topo)
+    s = InputParameters(params)
+    assert s.model["mode"] == "csem" and s.run["nord"] == 1 and s.run["cuda"] is True
+    assert s.run["num_polarizations"] == 1 and s.run["conductivity_from_file"] is False
+    assert os.path.isdir(s.output["directory"]) and os.path.isdir(s.output["directory_scratch"])
+    bad = str(tmp_path / "bad.yaml")
+    open(bad, "w").write(open(params).read().replace("nord: 1", "nord: 9"))
+    with pytest.raises(SystemExit):
+        InputParameters(bad)
+
+
+def test_petsc_binary_roundtrip_and_reference_fixture(tmp_path):
+    from petgem_b200 import parallel as par
+
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(7, 5))
+    f = str(tmp_path / "m.dat")
+    par.writeParallelDenseMatrix(f, par.createSequentialDenseMatrixWithArray(7, 5, a))
+    m = par.readPetscMatrix(f)
+    assert m.getSize() == (7, 5) and np.array_equal(m.array.real, a) and not m.array.imag.any()
+    cols, row = m.getRow(3)
+    assert np.array_equal(row.real, a[3]) and np.array_equal(cols, np.arange(5))
+    raw = open(f, "rb").read()
+    assert np.frombuffer(raw[:16], dtype=">i4").tolist() == [1211216, 7, 5, 35]  # PETSc MAT_FILE_CLASSID layout
+    v = rng.normal(size=11) + 1j * rng.normal(size=11)
+    g = str(tmp_path / "v.dat")
+    par.writePetscVector(g, par.createSequentialVectorWithArray(v))
+    assert np.array_equal(par.readPetscVector(g).getArray(), v)
+    assert np.frombuffer(open(g, "rb").read()[:8], dtype=">i4").tolist() == [1211214, 11]
+    # same bytes as the reference's own fixture reader would expect: write the golden system and re-read it
+    gold = golden("petsc_fixture_system.npz")
+    par.writePetscVector(g, par.createSequentialVectorWithArray(gold["b"]))
+    assert np.array_equal(par.readPetscVector(g).getArray(), gold["b"])
+
+
+def test_preprocessing_writes_reference_scratch_files(tmp_path, topo):
+    from petgem_b200 import parallel as par
+    from petgem_b200.common import InputParameters
+    from petgem_b200.preprocessing import Preprocessing
+
+    params, _ = make_case(tmp_path, topo, nord=2)
+    setup = InputParameters(params)
+    Preprocessing().run(setup)
+    tmp = setup.output["directory_scratch"]
+    T = 9453
+    assert np.array_equal(par.readPetscMatrix(tmp + "/edges.dat").array.real.astype(np.int64), topo["elemsE"])
+    assert np.array_equal(par.readPetscMatrix(tmp + "/faces.dat").array.real.astype(np.int64), topo["elemsF"])
+    fe = par.readPetscMatrix(tmp + "/facesEdges.dat").array.real.astype(np.int64)
+    assert np.array_equal(fe, topo["facesE"][topo["elemsF"]].reshape(T, 12))
+    dofs = par.readPetscMatrix(tmp + "/dofs.dat").array.real.astype(np.int64)
+    assert dofs.shape == (T, 20) and np.array_equal(dofs[topo["dofs_sel"]], topo["dofs_rows_p2"])
+    bd = par.readPetscVector(tmp + "/boundaries.dat").getArray().real.astype(np.int64)
+    assert np.array_equal(bd, topo["boundary_dofs_p2"])
+    src = par.readPetscVector(tmp + "/source.dat").getArray().real
+    assert src.size == 70 and np.array_equal(src[:4].astype(np.int64), topo["elemsN"][8946])
+    nnz = par.readPetscVector(tmp + "/nnz.dat").getArray().real
+    assert nnz.size == int(topo["total_dofs_p2"]) and (nnz == 200).all()
+    sig = par.readPetscMatrix(tmp + "/conductivityModel.dat").array.real
+    assert np.array_equal(sig[:, 0], np.array([1.0, 0.01, 1.0, 3.3333])[topo["tags"] - 1])
+
+
+def test_cpu_matrix_type_fails_loudly():
+    from petgem_b200 import parallel as par
+
+    with pytest.raises(SystemExit):
+        par.createParallelMatrix(10, 10, None, False)
+    with pytest.raises(SystemExit):
+        par.createParallelVector(10, False)
+
+
+@pytest.mark.gpu
+def test_kernel_cli_end_to_end(tmp_path, topo, oracle):
+    """python3 kernel.py -options_file petsc.opts params.yaml on the reference's test mesh (case1
+    physics, p=1): receiver E-fields within 1e-6 of a direct solve of the oracle's system."""
+    import scipy.sparse.linalg as spla
+
+    params, opts = make_case(tmp_path, topo, nord=1)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = np.load(str(tmp_path / "out" / "fields.npz"))
+    E = out["fields_0"]
+    # oracle: assemble with the reference algorithm restated on the CPU, direct solve
+    p, omega, mu = 1, 2 * np.pi * 2.0, 4e-7 * np.pi
+    nodes, elemsN, elemsE, elemsF = topo["nodes"], topo["elemsN"], topo["elemsE"], topo["elemsF"]
+    edgesNodes, facesE, tags = topo["edgesNodes"], topo["facesE"], topo["tags"]
+    T = elemsN.shape[0]
+    sig = np.array([1.0, 0.01, 1.0, 3.3333])
+    Ae = np.zeros((T, 6, 6), dtype=np.complex128)
+    for t in range(T):
+        s = sig[tags[t] - 1]
+        Ae[t] = oracle.element_system(nodes[elemsN[t]], elemsN[t], elemsE[t], edgesNodes[elemsE[t]],
+                                      facesE[elemsF[t]], np.array([s, s]), p, omega, mu)
+    dofs, *_ , N = oracle.compute_connectivity_dofs(elemsE.astype(np.int64), elemsF.astype(np.int64), p)
+    rp, ci, v = oracle.assemble_global(Ae, dofs, N)
+    bd = topo["boundary_dofs_p1"]
+    v = oracle.zero_rows_columns(rp, ci, v, bd, 1.0)
+    src = np.array([1750.0, 1750.0, -975.0])
+    t = 8946
+    b = oracle.csem_rhs(N, nodes[elemsN[t]], elemsN[t], elemsE[t], edgesNodes[elemsE[t]], facesE[elemsF[t]], dofs[t],
+                        p, src, 0.0, 0.0, 1.0, 1.0, omega, mu)
+    b[bd] = 0.0
+    xd = spla.spsolve(oracle.to_scipy(rp, ci, v).tocsc(), b)
+    rec = golden("case1_receivers.npy")
+    Ed = oracle.field_interpolator(xd, nodes, elemsN, elemsE, edgesNodes, elemsF, facesE, dofs, rec, p, omega, mu)
+    assert E.shape == Ed.shape
+    assert np.abs(E[:, :3] - Ed[:, :3]).max() <= 1e-6 * np.abs(Ed[:, :3]).max()
+    assert np.abs(E[:, 3:] - Ed[:, 3:]).max() <= 1e-6 * np.abs(Ed[:, 3:]).max()
+    # x0.dat is a PETSc binary Vec the reference Postprocessing could read (solver.py:593-594)
+    from petgem_b200.parallel import readPetscVector
+    x = readPetscVector(str(tmp_path / "tmp" / "x0.dat")).getArray()
+    assert np.linalg.norm(x - xd) <= 1e-6 * np.linalg.norm(xd)

@@ -141,3 +141,32 @@ def test_petsc_options_parser():
 
     o = parse_petsc_options("# Solver options for PETSc\n-ksp_type gmres\n-pc_type sor\n-ksp_rtol 1e-8\n-ksp_monitor\n")
     assert o == {"ksp_type": "gmres", "pc_type": "sor", "ksp_rtol": "1e-8", "ksp_monitor": True}
+
+
+def test_p2_reduced_face_functions():
+    """At p=2 the two functions of a face under any of the 6 orientations are +-2 of the 3 base
+    functions (orientation 0 family 0/1, orientation 1 family 1): the table the p=2 kernel keeps in
+    shared memory (pg_assemble.cu kFaceLut2)."""
+    lut = [0, 1, 1, 2, 2, 0, 6, 5, 4, 6, 5, 4]  # entry o*2+fam: base | neg<<2
+    lay = basis.expanded_layout(2)
+    pts = np.random.default_rng(1).dirichlet(np.ones(4), size=6)[:, :3]
+    N, C = basis.evaluate_expanded(2, pts)
+    X = lambda f, o, fam: lay["face_off"] + (f * 6 + o) * 2 + fam  # noqa: E731
+    for f in range(4):
+        base = [X(f, 0, 0), X(f, 0, 1), X(f, 1, 1)]
+        for o in range(6):
+            for fam in range(2):
+                e = lut[o * 2 + fam]
+                s = -1.0 if e & 4 else 1.0
+                assert np.abs(N[X(f, o, fam)] - s * N[base[e & 3]]).max() < 1e-14
+                assert np.abs(C[X(f, o, fam)] - s * C[base[e & 3]]).max() < 1e-14
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_reference_tensors_are_small_integers(p):
+    """SK*DK and SM*DM are exact small integers: what lets the p<=2 kernel hold the table as int16."""
+    nM, nK, err = basis.integer_tables(p)
+    assert err < 1e-9
+    assert max(np.abs(nM).max(), np.abs(nK).max()) < 32768
+    if p == 2:
+        assert np.abs(nM).max() == 252 and np.abs(nK).max() == 160
