@@ -210,13 +210,102 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+# ---------------------------------------------------------------------------------------------
+# time-to-solution per CSEM source on BASELINE configs[1] (~1 M tets, p=1, single source, 1 GPU)
+# ---------------------------------------------------------------------------------------------
+def csem_rhs_device(tab, p, plan, dev):
+    """b for a unit x-directed dipole at the centroid of the element nearest to the box centre
+    (solver.py:247-316), in the plan's numbering, owned rows only; Dirichlet rows zeroed."""
+    import torch
+
+    from petgem_b200 import hvfem
+
+    src = np.array([1750.0, 1750.0, -975.0])
+    cen = tab["nodes"][tab["elemsN"]].mean(axis=1)
+    te = int(np.argmin(((cen - src) ** 2).sum(axis=1)))
+    Xe = tab["nodes"][tab["elemsN"][te]]
+    J, Ji = hvfem.computeJacobian(Xe)
+    eo, fo = hvfem.computeElementOrientation(tab["elemsE"][te], tab["elemsN"][te],
+                                             tab["edgesNodes"][tab["elemsE"][te]], tab["facesE"][tab["elemsF"][te]])
+    basis_, _ = hvfem.computeBasisFunctions(eo, fo, J, Ji, p, np.array([0.25, 0.25, 0.25]))
+    de = hvfem.dofs_of_elements(tab["elemsE"][te], tab["elemsF"][te], [te], tab["nEdges"], tab["nFaces"], p)[0]
+    rhs = 1j * OMEGA * MU * (np.array([1.0, 0.0, 0.0]) @ basis_[:, :, 0])
+    perm = plan.dof_permutation()
+    b = torch.zeros((plan.local_rows,), dtype=torch.complex128, device=dev)
+    gi = perm[torch.as_tensor(de, device=dev)].to(torch.int64) - plan.row_begin
+    ok = (gi >= 0) & (gi < plan.local_rows)
+    b[gi[ok]] = torch.as_tensor(rhs, device=dev)[ok]
+    return b
+
+
+def time_to_solution(dev, m=55, p=1, maxit=20000):
+    """Assembly + Krylov solve to rtol 1e-8 (examples/case1/petsc.opts: gmres, rtol 1e-8; Jacobi
+    instead of SOR) for one source, wall clock with a device synchronize on both sides."""
+    import torch
+
+    from petgem_b200 import krylov
+    from petgem_b200.device import AssemblyPlan, CSRMatrix, ElementData
+
+    tab = build_case(m, p)
+    rows = host_rows(tab)
+    el = ElementData(rows["nodes"], rows["elemsN"], rows["elemsE"], rows["edgesNodes"], rows["facesEdges"],
+                     rows["elemsF"], rows["sigma"], tab["nEdges"], tab["nFaces"], device=dev)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    plan = AssemblyPlan(el, p, order="locality")
+    plan.set_dirichlet(bd_entities(tab, p, plan.nEnt))
+    rowptr, colidx = plan.csr()
+    torch.cuda.synchronize()
+    t_sym = time.time() - t0
+    t0 = time.time()
+    g, c = el.geometry()
+    vals = plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0)
+    torch.cuda.synchronize()
+    t_asm = time.time() - t0
+    A = CSRMatrix(rowptr, colidx, vals, plan.N)
+    b = csem_rhs_device(tab, p, plan, dev)
+    out = {"config": "synthetic layered-earth CSEM box, m=%d -> %d tets, p=%d, %d dofs (BASELINE configs[1])"
+                     % (m, tab["elemsN"].shape[0], p, plan.N),
+           "symbolic_s": t_sym, "assembly_s": t_asm}
+    for name, opts in (("gmres(30)+jacobi", {"ksp_type": "gmres"}), ("cocg+jacobi", {"ksp_type": "cg"})):
+        opts.update({"pc_type": "jacobi", "ksp_rtol": 1e-8, "ksp_max_it": maxit})
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = krylov.solve(A, b, opts)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        r = b - A.mult(res.x)
+        out[name] = {"seconds": dt, "iterations": res.iterations, "converged": bool(res.converged),
+                     "true_rel_residual": float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(b)),
+                     "time_to_solution_s": t_asm + dt}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level prints (e.g. "NCCL version ...") must not pollute the JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -227,6 +316,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--solve-maxit", type=int, default=600)
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-tts", action="store_true")
+    ap.add_argument("--tts-m", type=int, default=55, help="box size of the time-to-solution case (55 = C2)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--order", default="locality", choices=["locality", "reference"])
     args = ap.parse_args()
@@ -288,10 +379,11 @@ def main():
     torch.cuda.synchronize()
     symbolic_s = time.time() - t0
     vals = torch.empty((plan.nnz,), dtype=torch.complex128, device=dev)
-    geo, code = el.geometry()
+    erange = plan.element_range  # elements incident to the owned rows (all of them on one GPU)
+    gbuf = el.geometry(erange)
 
     def step():
-        g, c = el.geometry()
+        g, c = el.geometry(erange, out=gbuf)
         plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0, out=vals)
 
     # ---- timed region: K assembly steps ----------------------------------------------------------
@@ -305,7 +397,7 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev[0].record()
     for i in range(args.steps):
-        g, c = el.geometry()
+        g, c = el.geometry(erange, out=gbuf)
         kev[i][0].record()
         plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0, out=vals)
         kev[i][1].record()
@@ -354,24 +446,7 @@ def main():
     # ---- bounded Krylov run: time per GMRES iteration, time-to-solution if it converges -------------
     solve = None
     if not args.no_solve:
-        from petgem_b200 import hvfem
-
-        src = np.array([1750.0, 1750.0, -975.0])
-        b = torch.zeros((plan.local_rows,), dtype=torch.complex128, device=dev)
-        # unit x-directed dipole in the element containing the box centre (solver.py:247-316)
-        cen = tab["nodes"][tab["elemsN"]].mean(axis=1)
-        te = int(np.argmin(((cen - src) ** 2).sum(axis=1)))
-        Xe = tab["nodes"][tab["elemsN"][te]]
-        J, Ji = hvfem.computeJacobian(Xe)
-        eo, fo = hvfem.computeElementOrientation(tab["elemsE"][te], tab["elemsN"][te],
-                                                 tab["edgesNodes"][tab["elemsE"][te]], tab["facesE"][tab["elemsF"][te]])
-        basis_, _ = hvfem.computeBasisFunctions(eo, fo, J, Ji, p, np.array([0.25, 0.25, 0.25]))  # element centroid
-        perm = plan.dof_permutation()
-        de = hvfem.dofs_of_elements(tab["elemsE"][te], tab["elemsF"][te], [te], tab["nEdges"], tab["nFaces"], p)[0]
-        rhs = 1j * OMEGA * MU * (np.array([1.0, 0.0, 0.0]) @ basis_[:, :, 0])
-        gi = perm[torch.as_tensor(de, device=dev)].to(torch.int64) - plan.row_begin
-        ok = (gi >= 0) & (gi < plan.local_rows)
-        b[gi[ok]] = torch.as_tensor(rhs, device=dev)[ok]
+        b = csem_rhs_device(tab, p, plan, dev)
         barrier()
         t0 = time.time()
         res = krylov.gmres(op, b, rtol=1e-8, restart=30, maxit=args.solve_maxit)
@@ -380,6 +455,11 @@ def main():
         solve = {"ksp": "gmres(30)+jacobi", "rtol": 1e-8, "iterations": res.iterations, "converged": bool(res.converged),
                  "rel_residual": res.residuals[-1] / res.residuals[0] if res.residuals[0] else 0.0,
                  "seconds": dt, "ms_per_iteration": 1e3 * dt / max(res.iterations, 1)}
+
+    # ---- time-to-solution on configs[1] (1 GPU only) ---------------------------------------------------
+    tts = None
+    if world == 1 and not args.no_solve and not args.no_tts:
+        tts = time_to_solution(dev, m=args.tts_m, p=1)
 
     # ---- e2e through the public API with host buffers -----------------------------------------------
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in rows.items()}
@@ -390,7 +470,7 @@ def main():
         d = {k: t.to(dev, non_blocking=True) for k, t in pinned.items()}
         el.nodes, el.elemsN, el.elemsE, el.edgesNodes = d["nodes"], d["elemsN"], d["elemsE"], d["edgesNodes"]
         el.facesEdges, el.elemsF, el.sigma = d["facesEdges"], d["elemsF"], d["sigma"]
-        g, c = el.geometry()
+        g, c = el.geometry(erange, out=gbuf)
         plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0, out=vals)
         diag_host.copy_(A.diagonal(), non_blocking=True)
 
@@ -436,10 +516,10 @@ def main():
                        "l2": "inputs (%.1f GB) and output (%.1f GB) larger than L2; no flush needed"
                              % (T * 0.364e-6 * 1e3 / 1e3, plan.nnz * 16e-9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps,
-            "clocks": clocks, "spmv": spmv, "solve": solve,
+            "clocks": clocks, "spmv": spmv, "solve": solve, "tts": tts,
             "setup": {"host_mesh_s": tab["host_prep_s"], "symbolic_s": symbolic_s},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

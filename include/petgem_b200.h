@@ -123,6 +123,9 @@ int64_t pg_plan_row_begin(const pg_plan *plan);
 int64_t pg_plan_nnz(const pg_plan *plan);           /* nnz of the owned rows */
 int64_t pg_plan_contributions(const pg_plan *plan); /* sum over owned rows of element contributions */
 int pg_plan_max_row_length(const pg_plan *plan);
+/* smallest element range [*t_begin, *t_end) containing every element incident to an owned row: the
+ * only elements whose geometry (pg_element_geometry) this process needs */
+int pg_plan_element_range(const pg_plan *plan, int64_t *t_begin, int64_t *t_end);
 
 /* CSR of the owned rows: rowptr [local_rows+1] i64 (starting at 0), colidx [nnz] i32 (global cols) */
 int pg_plan_csr(const pg_plan *plan, int64_t *rowptr, int32_t *colidx, void *stream);
@@ -187,6 +190,8 @@ int pg_zpointwise_mult(int64_t n, const double *x, const double *y, double *z, v
 /* out[0] = sum conj(x_i) y_i  (VecDot(y,x) convention: PETSc conjugates the 2nd arg);
  * deterministic two-stage tree, work = pg_reduce_workspace_bytes() */
 int pg_zdotc(int64_t n, const double *x, const double *y, double *out, void *work, void *stream);
+/* out[0] = sum x_i y_i (VecTDot, no conjugation: the inner product of COCG on the complex symmetric A) */
+int pg_zdotu(int64_t n, const double *x, const double *y, double *out, void *work, void *stream);
 /* VecMDot: out[i] = sum conj(V_i) . w for k vectors V_i = V + i*ldv (complex elements), one pass over w */
 int pg_zmdotc(int64_t n, int k, const double *V, int64_t ldv, const double *w, double *out, void *work,
               void *stream);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "pg_plan_nnz": (_i64, [_p]),
     "pg_plan_contributions": (_i64, [_p]),
     "pg_plan_max_row_length": (C.c_int, [_p]),
+    "pg_plan_element_range": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "pg_plan_csr": (C.c_int, [_p, _p, _p, _p]),
     "pg_plan_dof_permutation": (C.c_int, [_p, _p, _p]),
     "pg_plan_entity_aligned_row": (_i64, [_p, _i64]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     "pg_zscal": (C.c_int, [_i64, _p, _i32, _p, _p]),
     "pg_zpointwise_mult": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_zdotc": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
+    "pg_zdotu": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "pg_zmdotc": (C.c_int, [_i64, _i32, _p, _i64, _p, _p, _p, _p]),
     "pg_zmaxpy": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p]),
     "pg_zmaxpy_nrm2sq": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p, _p, _p]),

@@ -214,6 +214,16 @@ __global__ void __launch_bounds__(kRedThreads) mdot_stage1(int64_t n, int kcount
     block_reduce_store<K>(acc, kcount, partial, kRedBlocks);
 }
 
+// unconjugated dot x^T y (COCG on the complex symmetric system)
+__global__ void __launch_bounds__(kRedThreads) dotu_stage1(int64_t n, const double2 *__restrict__ x,
+                                                           const double2 *__restrict__ y,
+                                                           double2 *__restrict__ partial) {
+    double2 acc[1] = {make_double2(0.0, 0.0)};
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        cfma(acc[0], x[j], y[j]);
+    block_reduce_store<1>(acc, 1, partial, kRedBlocks);
+}
+
 __global__ void __launch_bounds__(kRedThreads) nrm2_stage1(int64_t n, const double2 *__restrict__ x,
                                                            double2 *__restrict__ partial) {
     double2 acc[1] = {make_double2(0.0, 0.0)};
@@ -411,6 +421,16 @@ int pg_zmdotc(int64_t n, int k, const double *V, int64_t ldv, const double *w, d
 
 int pg_zdotc(int64_t n, const double *x, const double *y, double *out, void *work, void *stream) {
     return pg_zmdotc(n, 1, x, 0, y, out, work, stream);
+}
+
+int pg_zdotu(int64_t n, const double *x, const double *y, double *out, void *work, void *stream) {
+    PG_REQUIRE(n >= 0 && x && y && out && work, PG_EINVAL, "pg_zdotu: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dotu_stage1<<<kRedBlocks, kRedThreads, 0, st>>>(n, CD2(x), CD2(y), D2(work));
+    PG_LAUNCH_OK();
+    reduce_stage2<<<1, kRedThreads, 0, st>>>(D2(work), D2(out));
+    PG_LAUNCH_OK();
+    return PG_OK;
 }
 
 int pg_dznrm2sq(int64_t n, const double *x, double *out, void *work, void *stream) {

@@ -173,6 +173,20 @@ __global__ void block_lengths_kernel(int64_t b0, int64_t b1, int n, const int32_
     contrib[b - b0] = r * (int64_t)(inc_ptr[g + 1] - inc_ptr[g]) * n;
 }
 
+// element range touched by the owned blocks (records of an entity are sorted by element)
+__global__ void elem_range_kernel(int64_t b0, int64_t b1, const int32_t *__restrict__ ent_order,
+                                  const int32_t *__restrict__ inc_ptr, const IncRecord *__restrict__ rec,
+                                  int *__restrict__ mm) {
+    int64_t b = b0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= b1) return;
+    const int32_t g = ent_order[b];
+    const int32_t a = inc_ptr[g], e = inc_ptr[g + 1];
+    if (e > a) {
+        atomicMin(mm, rec[a].elem);
+        atomicMax(mm + 1, rec[e - 1].elem);
+    }
+}
+
 // block range of a row range; res = {b0, b1, aligned_begin, aligned_end}
 __global__ void find_blocks_kernel(int64_t nEnt, const int64_t *__restrict__ row_base, int64_t row_begin,
                                    int64_t row_end, int64_t *res) {
@@ -573,6 +587,17 @@ int pg_plan_create(int64_t T, int p, const int32_t *elemsE, const int32_t *elems
         PG_CUDA_OK(cub::DeviceReduce::Max(t4.p, bytes2, pl->rowlen, mx.as<int32_t>(), nEnt, st));
         PG_CUDA_OK(cudaMemcpyAsync(&pl->max_rowlen, mx.p, 4, cudaMemcpyDeviceToHost, st));
         PG_CUDA_OK(cudaMemcpyAsync(&pl->nnz, pl->valoff + nb, 8, cudaMemcpyDeviceToHost, st));
+        DevBuf mm;
+        int hmm[2] = {2147483647, -1};
+        PG_CUDA_OK(cudaMalloc(&mm.p, 8));
+        PG_CUDA_OK(cudaMemcpyAsync(mm.p, hmm, 8, cudaMemcpyHostToDevice, st));
+        elem_range_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(pl->b0, pl->b1, pl->ent_order, pl->inc_ptr,
+                                                                       pl->rec, mm.as<int>());
+        PG_LAUNCH_OK();
+        PG_CUDA_OK(cudaMemcpyAsync(hmm, mm.p, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA_OK(cudaStreamSynchronize(st));
+        pl->elem_begin = hmm[1] >= 0 ? hmm[0] : 0;
+        pl->elem_end = hmm[1] >= 0 ? hmm[1] + 1 : 0;
         PG_CUDA_OK(cudaStreamSynchronize(st));
     }
     PG_CUDA_OK(cudaStreamSynchronize(st));
@@ -590,6 +615,12 @@ int64_t pg_plan_row_begin(const pg_plan *pl) { return pl ? pl->row_begin : -1; }
 int64_t pg_plan_nnz(const pg_plan *pl) { return pl ? pl->nnz : -1; }
 int64_t pg_plan_contributions(const pg_plan *pl) { return pl ? pl->contributions : -1; }
 int pg_plan_max_row_length(const pg_plan *pl) { return pl ? pl->max_rowlen : -1; }
+int pg_plan_element_range(const pg_plan *pl, int64_t *t0, int64_t *t1) {
+    PG_REQUIRE(pl && t0 && t1, PG_EINVAL, "pg_plan_element_range: null pointer");
+    *t0 = pl->elem_begin;
+    *t1 = pl->elem_end;
+    return PG_OK;
+}
 
 int pg_plan_csr(const pg_plan *pl, int64_t *rowptr, int32_t *colidx, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -56,6 +56,7 @@ struct pg_plan {
     int64_t *valoff = nullptr;      // [b1-b0+1] offset into vals of the first row of owned block
     pg::EntHdr *hdr = nullptr;      // [b1-b0] headers in processing order
     int64_t nnz = 0, contributions = 0;
+    int64_t elem_begin = 0, elem_end = 0;  // range of elements incident to owned rows
     int max_rowlen = 0;
     uint8_t *bd_entity = nullptr;   // [nEnt] own copy, set by pg_plan_set_dirichlet
 };

@@ -86,17 +86,25 @@ class ElementData:
             device=device,
         )
 
-    def geometry(self):
-        """computeJacobian + computeElementOrientation for every element -> (geo [T,12], code [T])."""
-        geo = torch.empty((self.T, 12), dtype=torch.float64, device=self.device)
-        code = torch.empty((self.T,), dtype=torch.int32, device=self.device)
-        check(
-            lib().pg_element_geometry(
-                self.T, ptr(self.nodes), ptr(self.elemsN), ptr(self.elemsE), ptr(self.edgesNodes),
-                ptr(self.facesEdges), ptr(self.sigma), ptr(geo), ptr(code), stream_ptr(),
-            ),
-            "pg_element_geometry",
-        )
+    def geometry(self, elem_range=None, out=None):
+        """computeJacobian + computeElementOrientation -> (geo [T,12], code [T]).  With elem_range
+        (t0, t1) only those elements are evaluated (a rank needs just the elements touching its rows);
+        the arrays keep their global shape so that element ids index them directly."""
+        if out is None:
+            geo = torch.empty((self.T, 12), dtype=torch.float64, device=self.device)
+            code = torch.empty((self.T,), dtype=torch.int32, device=self.device)
+        else:
+            geo, code = out
+        t0, t1 = (0, self.T) if elem_range is None else elem_range
+        if t1 > t0:
+            check(
+                lib().pg_element_geometry(
+                    t1 - t0, ptr(self.nodes[t0:]), ptr(self.elemsN[t0:]), ptr(self.elemsE[t0:]),
+                    ptr(self.edgesNodes[t0:]), ptr(self.facesEdges[t0:]), ptr(self.sigma[t0:]), ptr(geo[t0:]),
+                    ptr(code[t0:]), stream_ptr(),
+                ),
+                "pg_element_geometry",
+            )
         return geo, code
 
     def dofs(self, p: int) -> torch.Tensor:
@@ -176,6 +184,9 @@ class AssemblyPlan:
         self.nnz = L.pg_plan_nnz(handle)
         self.contributions = L.pg_plan_contributions(handle)
         self.max_row_length = L.pg_plan_max_row_length(handle)
+        t0, t1 = C.c_int64(), C.c_int64()
+        check(L.pg_plan_element_range(handle, C.byref(t0), C.byref(t1)), "pg_plan_element_range")
+        self.element_range = (int(t0.value), int(t1.value))
         self._csr = None
 
     def __del__(self):

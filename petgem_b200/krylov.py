@@ -53,11 +53,47 @@ class DistContext:
     def allreduce(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(torch.view_as_real(t), op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def build_halo(self, colidx: torch.Tensor):
+        """Neighbour halo instead of the full all-gather (what PETSc's VecScatter does for MatMult).
+
+        Returns (colidx_local, send_idx, send_splits, recv_splits): columns remapped into
+        [own rows | received halo entries], the local row indices this rank must send (grouped by
+        destination rank) and the per-rank counts for all_to_all_single.  With the element-major
+        internal numbering the halo is the thin interface between spatial slabs."""
+        dev = colidx.device
+        lo, hi = self.row_begins[self.rank], self.row_begins[self.rank + 1]
+        c = colidx.to(torch.int64)
+        outside = (c < lo) | (c >= hi)
+        ext = torch.unique(c[outside])  # sorted global columns owned by other ranks
+        starts = torch.tensor(self.row_begins[:-1], dtype=torch.int64, device=dev)
+        owner = torch.bucketize(ext, starts, right=True) - 1
+        recv_counts = torch.bincount(owner, minlength=self.world)
+        send_counts = torch.empty_like(recv_counts)
+        self.dist.all_to_all_single(send_counts, recv_counts, group=self.group)
+        recv_splits, send_splits = recv_counts.tolist(), send_counts.tolist()
+        wanted = torch.empty((int(sum(send_splits)),), dtype=torch.int64, device=dev)
+        self.dist.all_to_all_single(wanted, ext, output_split_sizes=send_splits, input_split_sizes=recv_splits,
+                                    group=self.group)
+        send_idx = wanted - lo  # rows of mine the others asked for, grouped by destination
+        n = hi - lo
+        local = torch.where(outside, n + torch.searchsorted(ext, c), c - lo)
+        return local.to(torch.int32), send_idx, send_splits, recv_splits
+
+    def exchange(self, x_local, send_idx, send_splits, recv_splits, sendbuf, xbuf):
+        """xbuf = [x_local | halo]: pack, all_to_all over NCCL, unpack in place."""
+        n = x_local.numel()
+        xbuf[:n].copy_(x_local)
+        torch.index_select(x_local, 0, send_idx, out=sendbuf)
+        self.dist.all_to_all_single(torch.view_as_real(xbuf[n:]).view(-1), torch.view_as_real(sendbuf).view(-1),
+                                    output_split_sizes=[2 * s for s in recv_splits],
+                                    input_split_sizes=[2 * s for s in send_splits], group=self.group)
+        return xbuf
+
 
 class Operator:
     """y = M^-1 A x on the owned rows, with the halo handled for the caller."""
 
-    def __init__(self, A: CSRMatrix, pc: str = "none", ctx: DistContext = None):
+    def __init__(self, A: CSRMatrix, pc: str = "none", ctx: DistContext = None, halo: str = "auto"):
         self.A, self.ctx = A, ctx
         self.n = A.rows
         dev = A.vals.device
@@ -68,15 +104,34 @@ class Operator:
             self.inv_diag = torch.where(d == 0, torch.ones_like(d), 1.0 / d)  # PCJACOBI: zero diagonal -> 1
         elif pc != "none":
             raise ValueError("unsupported preconditioner %r (none, jacobi)" % pc)
+        self.mode = "single"
         if ctx is not None and ctx.world > 1:
-            self.colidx_local = ctx.remap_columns(A.colidx)
-            self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
-            self.full = torch.zeros((ctx.world * ctx.max_rows,), dtype=_C128, device=dev)
-            self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin)
+            # x exchange before the SpMV: neighbour halo (packed all_to_all) when the off-block column
+            # set is small -- the case with the element-major numbering -- else all-gather of x
+            self.mode = halo
+            if halo in ("auto", "p2p"):
+                col_l, self.send_idx, self.send_splits, self.recv_splits = ctx.build_halo(A.colidx)
+                next_ = int(sum(self.recv_splits))
+                frac = torch.tensor([next_ / max(self.n, 1)], dtype=torch.float64, device=dev)
+                ctx.dist.all_reduce(frac, op=ctx.dist.ReduceOp.MAX, group=ctx.group)
+                self.mode = "p2p" if (halo == "p2p" or frac.item() < 0.5) else "allgather"
+                if self.mode == "p2p":
+                    self.halo_entries = next_
+                    self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
+                    self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
+                    self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin)
+            if self.mode == "allgather":
+                self.colidx_local = ctx.remap_columns(A.colidx)
+                self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
+                self.full = torch.zeros((ctx.world * ctx.max_rows,), dtype=_C128, device=dev)
+                self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin)
         self.spmv_calls = 0
 
     def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
-        if self.ctx is not None and self.ctx.world > 1:
+        if self.mode == "p2p":
+            self.ctx.exchange(x, self.send_idx, self.send_splits, self.recv_splits, self.sendbuf, self.xbuf)
+            self.A_halo.mult(self.xbuf, y, row_scale)
+        elif self.mode == "allgather":
             self.ctx.gather(x, self.send, self.full)
             self.A_halo.mult(self.full, y, row_scale)
         else:
@@ -114,6 +169,13 @@ class VecKernels:
     def dot(self, x, y, out):
         """out[0] = sum conj(x) y."""
         check(lib().pg_zdotc(self.n, ptr(x), ptr(y), ptr(out), ptr(self.work), stream_ptr()), "pg_zdotc")
+        if self.ctx is not None and self.ctx.world > 1:
+            self.ctx.allreduce(out[:1])
+        return out
+
+    def dotu(self, x, y, out):
+        """out[0] = sum x y (no conjugation)."""
+        check(lib().pg_zdotu(self.n, ptr(x), ptr(y), ptr(out), ptr(self.work), stream_ptr()), "pg_zdotu")
         if self.ctx is not None and self.ctx.world > 1:
             self.ctx.allreduce(out[:1])
         return out
@@ -308,8 +370,8 @@ def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, moni
     sc = torch.zeros((8,), dtype=_C128, device=dev)
     one = torch.ones((1,), dtype=_C128, device=dev)
 
-    def udot(u, v):  # unconjugated u^T v = conj(conj(u))^T v
-        return complex(vk.dot(torch.conj_physical(u), v, sc)[0].item())
+    def udot(u, v):  # unconjugated u^T v
+        return complex(vk.dotu(u, v, sc)[0].item())
 
     op.precond(r, z)
     bnorm = math.sqrt(vk.nrm2sq(z, sc)[0].real.item())

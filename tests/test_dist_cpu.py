@@ -44,6 +44,15 @@ def _worker(rank, world, port, N, cuts, seed, out):
         Ah = sp.csr_matrix((Aloc.data, col_local, Aloc.indptr), shape=(hi - lo, world * ctx.max_rows))
         y = Ah @ full.numpy()
         assert np.abs(y - (A @ x)[lo:hi]).max() < 1e-12
+        # neighbour halo: [own | received] buffer and remapped columns give the same product
+        col_h, send_idx, send_splits, recv_splits = ctx.build_halo(torch.from_numpy(Aloc.indices.astype(np.int32)))
+        nloc, next_ = hi - lo, int(sum(recv_splits))
+        sendbuf = torch.zeros(int(sum(send_splits)), dtype=torch.complex128)
+        xbuf = torch.zeros(nloc + next_, dtype=torch.complex128)
+        ctx.exchange(torch.from_numpy(x[lo:hi].copy()), send_idx, send_splits, recv_splits, sendbuf, xbuf)
+        assert np.array_equal(xbuf.numpy()[col_h.numpy()], x[Aloc.indices])
+        Ap = sp.csr_matrix((Aloc.data, col_h.numpy(), Aloc.indptr), shape=(nloc, nloc + next_))
+        assert np.abs(Ap @ xbuf.numpy() - (A @ x)[lo:hi]).max() < 1e-12
         # all-reduced dot product equals the global one
         d = torch.tensor([np.vdot(x[lo:hi], y)], dtype=torch.complex128)
         ctx.allreduce(d)

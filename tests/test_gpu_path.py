@@ -395,6 +395,22 @@ def test_spmv_and_vector_kernels_match_numpy():
     y5 = wd.clone()
     vk.scal(ad[:1], y5)
     assert np.abs(y5.cpu().numpy() - alpha[0] * w).max() <= 1e-13 * np.abs(w).max() * 4
+    # fused kernels of the GMRES inner loop: MAXPY + norm, scaled copy, SpMV + Jacobi scaling
+    for k in (3, 8, 17):
+        w3 = wd.clone()
+        vk.maxpy_nrm2sq(k, ad, -1.0, Vd, n, w3, out[:1])
+        ref = w - alpha[:k] @ V[:k]
+        assert np.abs(w3.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+        assert abs(out[0].item().real - np.vdot(ref, ref).real) <= 1e-13 * np.vdot(ref, ref).real
+    nrm = torch.tensor([3.5 + 0j], dtype=torch.complex128, device=dev)
+    y6 = torch.empty_like(wd)
+    vk.copy_scaled(nrm, wd, y6, inv_real=True)
+    assert np.abs(y6.cpu().numpy() - w / 3.5).max() <= 1e-15 * np.abs(w).max()
+    vk.copy_scaled(ad[:1], wd, y6)
+    assert np.abs(y6.cpu().numpy() - alpha[0] * w).max() <= 1e-13 * np.abs(w).max() * 4
+    dsc = rng.normal(size=4184) + 1j * rng.normal(size=4184)
+    ys = A.mult(torch.as_tensor(x, device=dev), row_scale=torch.as_tensor(dsc, device=dev)).cpu().numpy()
+    assert np.abs(ys - dsc * yr).max() <= 1e-13 * np.abs(dsc * yr).max()
     # run-to-run determinism of the reductions
     o1, o2 = torch.zeros(32, dtype=torch.complex128, device=dev), torch.zeros(32, dtype=torch.complex128, device=dev)
     vk.mdot(31, Vd, n, wd, o1)
@@ -455,6 +471,13 @@ def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
     xo, its_o, _ = oracle.gmres(lambda v: As @ v, b, rtol=1e-8, pc=lambda v: dinv * v)
     res8 = krylov.solve(A, bd, {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-8})
     assert res8.converged and abs(res8.iterations - its_o) <= max(3, its_o // 50), (res8.iterations, its_o)
+    # A is complex symmetric: -ksp_type cg -ksp_cg_type symmetric (COCG) applies
+    resc = krylov.solve(A, bd, {"ksp_type": "cg", "ksp_cg_type": "symmetric", "pc_type": "jacobi",
+                                "ksp_rtol": 1e-12, "ksp_max_it": 20000})
+    assert resc.converged, (resc.reason, resc.iterations)
+    Ec = oracle.field_interpolator(resc.x.cpu().numpy(), topo["nodes"], topo["elemsN"], topo["elemsE"],
+                                   topo["edgesNodes"], topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
+    assert np.abs(Ec[:, :3] - Ed[:, :3]).max() <= 1e-6 * scale
     resb = krylov.solve(A, bd, {"ksp_type": "bcgs", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_max_it": 20000})
     if resb.converged:  # BiCGStab may break down on this system; when it converges it must agree
         Eb = oracle.field_interpolator(resb.x.cpu().numpy(), topo["nodes"], topo["elemsN"], topo["elemsE"],
