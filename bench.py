@@ -10,7 +10,7 @@ per-element geometry + orientation kernel, then the fused element-matrix +
 deterministic row-gather kernel with the Dirichlet condition applied (everything
 Solver.assembly + zeroRowsColumns do to A).  Inputs are resident in HBM for `value`;
 `e2e` repeats the step through the public API from pinned host arrays (H2D of the
-per-element rows, D2H of the assembled diagonal) inside the timed region.
+per-element rows, D2H of ||A||_F^2 reduced on the device) inside the timed region.
 
 Also reported (same JSON line): SpMV GB/s, GMRES iteration time and a bounded
 time-to-solution run, the roofline of the dominant kernel, and the CPU baseline
@@ -464,7 +464,12 @@ def main():
     # ---- e2e through the public API with host buffers -----------------------------------------------
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in rows.items()}
     h2d = sum(int(t.numel() * t.element_size()) for t in pinned.values())
-    diag_host = torch.empty((plan.local_rows,), dtype=torch.complex128).pin_memory()
+    # the step's result read back by the host: ||A||_F^2 of the assembled block (a 16-byte metric, like a
+    # loss), reduced on the device by pg_dznrm2sq
+    from petgem_b200._lib import check, ptr, stream_ptr
+    fro_host = torch.empty((1,), dtype=torch.complex128).pin_memory()
+    fro_dev = torch.zeros((1,), dtype=torch.complex128, device=dev)
+    fro_work = torch.empty((lib().pg_reduce_workspace_bytes(1) // 16,), dtype=torch.complex128, device=dev)
 
     def e2e_step():
         d = {k: t.to(dev, non_blocking=True) for k, t in pinned.items()}
@@ -472,7 +477,8 @@ def main():
         el.facesEdges, el.elemsF, el.sigma = d["facesEdges"], d["elemsF"], d["sigma"]
         g, c = el.geometry(erange, out=gbuf)
         plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0, out=vals)
-        diag_host.copy_(A.diagonal(), non_blocking=True)
+        check(lib().pg_dznrm2sq(plan.nnz, ptr(vals), ptr(fro_dev), ptr(fro_work), stream_ptr()), "pg_dznrm2sq")
+        fro_host.copy_(fro_dev, non_blocking=True)
 
     for _ in range(2):
         e2e_step()
@@ -487,7 +493,8 @@ def main():
     # the sampler ran over the timed assembly steps, the SpMV / Krylov section and the e2e steps
     clocks = sampler.stop() if rank == 0 else None
     e2e = {"value": T / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": int(plan.local_rows * 16), "ms_per_step": e2e_ms}
+           "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms,
+           "result": "squared Frobenius norm of the assembled matrix: %.17g" % fro_host[0].real.item()}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None

@@ -201,6 +201,9 @@ int pg_zmaxpy(int64_t n, int k, const double *alpha, double scale, const double 
 /* VecMAXPY followed by VecNorm of the result, fused: out[0] = sum |w_i|^2 after the update */
 int pg_zmaxpy_nrm2sq(int64_t n, int k, const double *alpha, double scale, const double *V, int64_t ldv, double *w,
                      double *out, void *work, void *stream);
+/* out[0] = a/b (negated when negate != 0), out[1] = -out[0]; device scalars: the Krylov coefficients
+ * (alpha = rho / p^T A p, beta = rho_new / rho) never visit the host */
+int pg_zdiv(const double *a, const double *b, int negate, double *out, void *stream);
 /* y = alpha x, or y = x / Re(alpha) when inv_real != 0 (VecCopy + VecScale fused) */
 int pg_zcopy_scaled(int64_t n, const double *alpha, int inv_real, const double *x, double *y, void *stream);
 /* out[0] = sum |x_i|^2 (real, stored as complex with zero imaginary part) */

@@ -93,6 +93,7 @@ SIGNATURES = {
     "pg_zmdotc": (C.c_int, [_i64, _i32, _p, _i64, _p, _p, _p, _p]),
     "pg_zmaxpy": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p]),
     "pg_zmaxpy_nrm2sq": (C.c_int, [_i64, _i32, _p, _d, _p, _i64, _p, _p, _p, _p]),
+    "pg_zdiv": (C.c_int, [_p, _p, _i32, _p, _p]),
     "pg_zcopy_scaled": (C.c_int, [_i64, _p, _i32, _p, _p, _p]),
     "pg_dznrm2sq": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_reduce_workspace_bytes": (_i64, [_i32]),

@@ -291,6 +291,17 @@ __global__ void __launch_bounds__(kRedThreads) maxpy_kernel(int64_t n, int kcoun
     if (NORM) block_reduce_store<1>(nrm, 1, partial, kRedBlocks);
 }
 
+// out[0] = +-a/b (and out[1] = -out[0]): Krylov coefficients formed on the device, no host round trip
+__global__ void zdiv_kernel(const double2 *__restrict__ a, const double2 *__restrict__ b, int negate,
+                            double2 *__restrict__ out) {
+    const double2 x = *a, y = *b;
+    const double den = y.x * y.x + y.y * y.y;
+    double2 q = make_double2((x.x * y.x + x.y * y.y) / den, (x.y * y.x - x.x * y.y) / den);
+    if (negate) q = make_double2(-q.x, -q.y);
+    out[0] = q;
+    out[1] = make_double2(-q.x, -q.y);
+}
+
 // y = alpha x, or y = x / Re(alpha) (VecCopy + VecScale of the GMRES normalisation, fused)
 __global__ void __launch_bounds__(256) zcopy_scaled_kernel(int64_t n, const double2 *__restrict__ alpha, int inv_real,
                                                            const double2 *__restrict__ x, double2 *__restrict__ y) {
@@ -474,6 +485,13 @@ int pg_zmaxpy_nrm2sq(int64_t n, int k, const double *alpha, double scale, const 
         PG_LAUNCH_OK();
     }
     reduce_stage2<<<1, kRedThreads, 0, st>>>(D2(work), D2(out));
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int pg_zdiv(const double *a, const double *b, int negate, double *out, void *stream) {
+    PG_REQUIRE(a && b && out, PG_EINVAL, "pg_zdiv: null pointer");
+    zdiv_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(CD2(a), CD2(b), negate, D2(out));
     PG_LAUNCH_OK();
     return PG_OK;
 }

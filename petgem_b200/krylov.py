@@ -359,48 +359,54 @@ def bicgstab(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, 
     return SolveResult(x, maxit, hist, False, "maxit")
 
 
-def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None):
+def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None, check_every=10):
     """Conjugate-orthogonal CG for the complex SYMMETRIC system (KSPCG with -ksp_cg_type symmetric):
     one SpMV, two unconjugated dots and three vector updates per iteration, no restart.  Jacobi enters
-    symmetrically through z = D^-1 r; convergence is tested on the preconditioned residual like PETSc."""
+    symmetrically through z = D^-1 r; convergence is tested on the preconditioned residual like PETSc.
+    All coefficients (alpha = rho / p^T A p, beta = rho' / rho) are formed on the device (pg_zdiv), so
+    the host synchronises only every `check_every` iterations to read the residual norm; the returned
+    iteration count is therefore rounded up to that granularity."""
     n, dev = op.n, b.device
     vk = VecKernels(n, dev, op.ctx, kmax=4)
     z_ = lambda: torch.zeros((n,), dtype=_C128, device=dev)  # noqa: E731
     x, r, z, p_, q = z_(), b.clone(), z_(), z_(), z_()
+    # device scalars: [0] rho  [1] rho_new  [2] p^T A p  [3] alpha  [4] -alpha  [5] beta  [6] -beta  [7] |z|^2
     sc = torch.zeros((8,), dtype=_C128, device=dev)
-    one = torch.ones((1,), dtype=_C128, device=dev)
-
-    def udot(u, v):  # unconjugated u^T v
-        return complex(vk.dotu(u, v, sc)[0].item())
+    zdiv = lib().pg_zdiv
 
     op.precond(r, z)
-    bnorm = math.sqrt(vk.nrm2sq(z, sc)[0].real.item())
+    bnorm = math.sqrt(vk.nrm2sq(z, sc[7:8])[0].real.item())
     if bnorm == 0.0:
         return SolveResult(x, 0, [0.0], True, "zero rhs")
     tol = max(rtol * bnorm, atol)
     p_.copy_(z)
-    rho = udot(r, z)
+    vk.dotu(r, z, sc[0:1])
     hist = [bnorm]
-    for it in range(1, maxit + 1):
-        op.matvec(p_, q)
-        den = udot(p_, q)
-        if den == 0.0 or rho == 0.0:
-            return SolveResult(x, it - 1, hist, False, "breakdown")
-        alpha = rho / den
-        sc[1], sc[2] = alpha, -alpha
-        vk.axpy(sc[1:2], p_, x)
-        vk.axpy(sc[2:3], q, r)
-        op.precond(r, z)
-        res = math.sqrt(vk.nrm2sq(z, sc)[0].real.item())
+    it = 0
+    rho_i, rho_new_i = 0, 1
+    while it < maxit:
+        for _ in range(min(check_every, maxit - it)):
+            op.matvec(p_, q)
+            vk.dotu(p_, q, sc[2:3])
+            check(zdiv(ptr(sc[rho_i:rho_i + 1]), ptr(sc[2:3]), 0, ptr(sc[3:5]), stream_ptr()), "pg_zdiv")
+            vk.axpy(sc[3:4], p_, x)          # x += alpha p
+            vk.axpy(sc[4:5], q, r)           # r -= alpha A p
+            op.precond(r, z)
+            vk.dotu(r, z, sc[rho_new_i:rho_new_i + 1])
+            check(zdiv(ptr(sc[rho_new_i:rho_new_i + 1]), ptr(sc[rho_i:rho_i + 1]), 0, ptr(sc[5:7]), stream_ptr()),
+                  "pg_zdiv")
+            vk.aypx(sc[5:6], z, p_)          # p = z + beta p
+            rho_i, rho_new_i = rho_new_i, rho_i
+            it += 1
+        res2 = vk.nrm2sq(z, sc[7:8])[0].real.item()  # the host sync of this batch
+        if not math.isfinite(res2):
+            return SolveResult(x, it, hist, False, "breakdown")
+        res = math.sqrt(res2)
         hist.append(res)
         if monitor:
             monitor(it, res)
         if res <= tol:
             return SolveResult(x, it, hist, True, "rtol")
-        rho_new = udot(r, z)
-        sc[1] = rho_new / rho
-        vk.aypx(sc[1:2], z, p_)  # p = z + beta p
-        rho = rho_new
     return SolveResult(x, maxit, hist, False, "maxit")
 
 
