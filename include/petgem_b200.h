@@ -172,6 +172,14 @@ int pg_spmv(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, co
 /* y = dscale .* (A x): MatMult fused with the PCJACOBI application (dscale = 1/diag, may be NULL) */
 int pg_spmv_scaled(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
                    const double *x, const double *dscale, double *y, void *stream);
+/* Entity-blocked MatMult for p = 2 (same result as pg_spmv_scaled on the plan's CSR): reads the plan's
+ * per-entity column lists (4 B per 2x2 block instead of 16 B of colidx).
+ *   colstart: NULL = the plan's own (global columns of the numbering in use), or a remapped copy of
+ *             pg_plan_column_starts() indexing a [own | halo] vector in multi-GPU runs */
+int pg_spmv_blocked(const pg_plan *plan, const int32_t *colstart, const double *vals, const double *x,
+                    const double *dscale, double *y, void *stream);
+int64_t pg_plan_num_column_entities(const pg_plan *plan);
+int pg_plan_column_starts(const pg_plan *plan, int32_t *colstart, void *stream);
 /* diag [local_rows] complex128 of the owned block (for PCJACOBI) */
 int pg_csr_diagonal(int64_t local_rows, int64_t row_begin, const int64_t *rowptr, const int32_t *colidx,
                     const double *vals, double *diag, void *stream);

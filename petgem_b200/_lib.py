@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -82,6 +82,9 @@ SIGNATURES = {
     "pg_zero_rows_columns": (C.c_int, [_i64, _i64, _p, _p, _p, _d, _p, _p]),
     "pg_spmv": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
     "pg_spmv_scaled": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
+    "pg_spmv_blocked": (C.c_int, [_p, _p, _p, _p, _p, _p, _p]),
+    "pg_plan_num_column_entities": (_i64, [_p]),
+    "pg_plan_column_starts": (C.c_int, [_p, _p, _p]),
     "pg_csr_diagonal": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p]),
     "pg_zaxpy": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_zaypx": (C.c_int, [_i64, _p, _p, _p, _p]),

@@ -4,6 +4,8 @@
 // VecPointwiseMult (PCJACOBI), and MatZeroRowsColumns (solver.py:562).
 // All reductions are fixed-shape two-stage trees (no atomics): results are
 // bit-reproducible run to run.
+#include <stdlib.h>
+
 #include "pg_common.cuh"
 
 namespace pg {
@@ -32,7 +34,7 @@ __device__ __forceinline__ unsigned group_mask() {
 // ---------------------------------------------------------------------------
 // SpMV: G lanes per row, coalesced (colidx, vals) streams, x gathered through L2
 // ---------------------------------------------------------------------------
-template <int G>
+template <int G, int HINT>
 __global__ void __launch_bounds__(256, 6) spmv_kernel(int64_t rows, const int64_t *__restrict__ rowptr,
                                                       const int32_t *__restrict__ colidx,
                                                       const double2 *__restrict__ vals,
@@ -42,25 +44,27 @@ __global__ void __launch_bounds__(256, 6) spmv_kernel(int64_t rows, const int64_
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
     const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
     const unsigned gm = group_mask<G>();
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
     for (int64_t row = grp; row < rows; row += ngrp) {
         const int64_t a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
         double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
         int64_t j = a + lane;
         // 4 independent (index, value, x) streams per lane: the kernel is latency bound otherwise
         for (; j + 3 * G < b; j += 4 * G) {
-            const int32_t c0 = __ldg(colidx + j), c1 = __ldg(colidx + j + G);
-            const int32_t c2 = __ldg(colidx + j + 2 * G), c3 = __ldg(colidx + j + 3 * G);
-            const double2 v0 = __ldcs(vals + j), v1 = __ldcs(vals + j + G);
-            const double2 v2 = __ldcs(vals + j + 2 * G), v3 = __ldcs(vals + j + 3 * G);
-            const double2 x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+            const int32_t c0 = ld_stream<HINT>(colidx + j, stream), c1 = ld_stream<HINT>(colidx + j + G, stream);
+            const int32_t c2 = ld_stream<HINT>(colidx + j + 2 * G, stream), c3 = ld_stream<HINT>(colidx + j + 3 * G, stream);
+            const double2 v0 = ld_stream<HINT>(vals + j, stream), v1 = ld_stream<HINT>(vals + j + G, stream);
+            const double2 v2 = ld_stream<HINT>(vals + j + 2 * G, stream), v3 = ld_stream<HINT>(vals + j + 3 * G, stream);
+            const double2 x0 = ld_keep<HINT>(x + c0, keep), x1 = ld_keep<HINT>(x + c1, keep);
+            const double2 x2 = ld_keep<HINT>(x + c2, keep), x3 = ld_keep<HINT>(x + c3, keep);
             cfma(acc0, v0, x0);
             cfma(acc1, v1, x1);
             cfma(acc0, v2, x2);
             cfma(acc1, v3, x3);
         }
         for (; j < b; j += G) {
-            const int32_t c0 = __ldg(colidx + j);
-            cfma(acc0, __ldcs(vals + j), __ldg(x + c0));
+            const int32_t c0 = ld_stream<HINT>(colidx + j, stream);
+            cfma(acc0, ld_stream<HINT>(vals + j, stream), ld_keep<HINT>(x + c0, keep));
         }
         acc0.x += acc1.x;
         acc0.y += acc1.y;
@@ -311,6 +315,14 @@ __global__ void __launch_bounds__(256) zcopy_scaled_kernel(int64_t n, const doub
         y[i] = cmul(al, x[i]);
 }
 
+int spmv_hint_mode() {
+    static const int mode = [] {
+        const char *e = getenv("PG_SPMV_HINTS");
+        return e ? atoi(e) : 1;  // measured (tools/spmv_bench.py): explicit evict-first on the streams wins
+    }();
+    return mode;
+}
+
 static inline unsigned ew_grid(int64_t n) {
     int64_t b = (n + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -340,7 +352,11 @@ int pg_spmv_scaled(int64_t rows, const int64_t *rowptr, const int32_t *colidx, c
     // the best trade-off for the 15..120 nnz/row of p=1..2; long rows are still coalesced)
     constexpr int G = 8;
     int64_t blocks = std::min<int64_t>((rows * G + 255) / 256, (int64_t)kNumSMs * 96);
-    spmv_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y));
+    switch (spmv_hint_mode()) {
+        case 1: spmv_kernel<G, 1><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
+        case 2: spmv_kernel<G, 2><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
+        default: spmv_kernel<G, 0><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y));
+    }
     PG_LAUNCH_OK();
     return PG_OK;
 }

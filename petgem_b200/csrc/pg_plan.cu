@@ -161,6 +161,13 @@ __global__ void __launch_bounds__(kSymWarps * 32)
     }
 }
 
+__global__ void colstart_kernel(int64_t n, const int32_t *__restrict__ colent,
+                                const int32_t *__restrict__ blk_of_ent, const int64_t *__restrict__ row_base,
+                                int32_t *__restrict__ colstart) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) colstart[i] = (int32_t)row_base[blk_of_ent[colent[i]]];
+}
+
 __global__ void block_lengths_kernel(int64_t b0, int64_t b1, int n, const int32_t *__restrict__ ent_order,
                                      const int32_t *__restrict__ rowlen, const int32_t *__restrict__ inc_ptr,
                                      const int64_t *__restrict__ row_base, int64_t *__restrict__ vlen,
@@ -291,7 +298,8 @@ __global__ void hdr_fill_kernel(int64_t b0, int64_t nb, const int32_t *__restric
                                 const int32_t *__restrict__ ent_order, const int64_t *__restrict__ row_base,
                                 const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ rowlen,
                                 const int32_t *__restrict__ selfpos, const int64_t *__restrict__ valoff,
-                                const uint8_t *__restrict__ bd_entity, EntHdr *__restrict__ hdr) {
+                                const int64_t *__restrict__ colent_ptr, const uint8_t *__restrict__ bd_entity,
+                                EntHdr *__restrict__ hdr) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nb) return;
     const int64_t bl = order[i];
@@ -305,7 +313,8 @@ __global__ void hdr_fill_kernel(int64_t b0, int64_t nb, const int32_t *__restric
     h.selfpos = (uint16_t)selfpos[g];
     h.bd = (bd_entity && bd_entity[g]) ? 1 : 0;
     h.rows = (uint8_t)(row_base[b0 + bl + 1] - row_base[b0 + bl]);
-    h.pad[0] = h.pad[1] = 0;
+    h.row = (int32_t)(row_base[b0 + bl] - row_base[b0]);
+    h.cbase = (int32_t)colent_ptr[g];
     hdr[i] = h;
 }
 
@@ -372,7 +381,7 @@ static int build_headers(pg_plan *pl, cudaStream_t st) {
     PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.as<int32_t>(), keys_out.as<int32_t>(),
                                                vals.as<int32_t>(), order.as<int32_t>(), nb, 0, bits, st));
     hdr_fill_kernel<<<grid, 256, 0, st>>>(pl->b0, nb, order.as<int32_t>(), pl->ent_order, pl->row_base, pl->inc_ptr,
-                                          pl->rowlen, pl->selfpos, pl->valoff, pl->bd_entity, pl->hdr);
+                                          pl->rowlen, pl->selfpos, pl->valoff, pl->colent_ptr, pl->bd_entity, pl->hdr);
     PG_LAUNCH_OK();
     PG_CUDA_OK(cudaStreamSynchronize(st));
     return PG_OK;
@@ -404,6 +413,7 @@ void pg_plan_destroy(pg_plan *pl) {
     cudaFree(pl->rec);
     cudaFree(pl->colent_ptr);
     cudaFree(pl->colent);
+    cudaFree(pl->colstart);
     cudaFree(pl->rowlen);
     cudaFree(pl->selfpos);
     cudaFree(pl->valoff);
@@ -550,6 +560,8 @@ int pg_plan_create(int64_t T, int p, const int32_t *elemsE, const int32_t *elems
     int64_t ncolent = 0;
     PG_CUDA_OK(cudaMemcpyAsync(&ncolent, pl->colent_ptr + nEnt, 8, cudaMemcpyDeviceToHost, st));
     PG_CUDA_OK(cudaStreamSynchronize(st));
+    PG_REQUIRE(ncolent < 2147483647LL, PG_ERANGE, "pg_plan_create: %lld column entities exceed int32",
+               (long long)ncolent);
     PG_REQUIRE(hflag[0] == 0, PG_ERANGE, "pg_plan_create: an entity has more than %d incident elements",
                kCandCap / PG_SLOTS);
     PG_CUDA_OK(cudaMalloc((void **)&pl->colent, std::max<int64_t>(ncolent, 1) * 4));
@@ -559,6 +571,14 @@ int pg_plan_create(int64_t T, int p, const int32_t *elemsE, const int32_t *elems
                                                      ncol.as<int32_t>(), pl->rowlen, pl->colent_ptr, pl->colent,
                                                      pl->selfpos, pl->rec, flag.as<int>() + 1);
     PG_LAUNCH_OK();
+
+    pl->ncolent = ncolent;
+    PG_CUDA_OK(cudaMalloc((void **)&pl->colstart, std::max<int64_t>(ncolent, 1) * 4));
+    if (ncolent > 0) {
+        colstart_kernel<<<(unsigned)((ncolent + 255) / 256), 256, 0, st>>>(ncolent, pl->colent, pl->blk_of_ent,
+                                                                          pl->row_base, pl->colstart);
+        PG_LAUNCH_OK();
+    }
 
     // --- value offsets of the owned blocks ---------------------------------------------
     const int64_t nb = pl->b1 - pl->b0;
@@ -644,6 +664,14 @@ int pg_plan_dof_permutation(const pg_plan *pl, int32_t *perm, void *stream) {
     dof_perm_kernel<<<(unsigned)((pl->nEnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         pl->nEnt, pl->p, pl->nE, pl->nF, pl->T, pl->blk_of_ent, pl->row_base, perm);
     PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int64_t pg_plan_num_column_entities(const pg_plan *pl) { return pl ? pl->ncolent : -1; }
+
+int pg_plan_column_starts(const pg_plan *pl, int32_t *out, void *stream) {
+    PG_REQUIRE(pl && out, PG_EINVAL, "pg_plan_column_starts: null pointer");
+    PG_CUDA_OK(cudaMemcpyAsync(out, pl->colstart, pl->ncolent * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return PG_OK;
 }
 

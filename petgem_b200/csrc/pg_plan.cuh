@@ -28,7 +28,8 @@ struct __align__(16) EntHdr {
     uint16_t selfpos;  // position of the entity's own dofs in its column list
     uint8_t bd;        // Dirichlet entity
     uint8_t rows;      // rows of the entity
-    int32_t pad[2];
+    int32_t row;       // first row of the entity, local to the owned block
+    int32_t cbase;     // first entry of the entity's column-entity list (colent / colstart)
 };
 static_assert(sizeof(EntHdr) == 32, "EntHdr must be 32 bytes");
 
@@ -49,6 +50,8 @@ struct pg_plan {
     // column-entity lists by entity id
     int64_t *colent_ptr = nullptr;  // [nEnt+1]
     int32_t *colent = nullptr;      // [ncolent] global entity ids, ascending block position
+    int32_t *colstart = nullptr;    // [ncolent] first column (numbering in use) of each column entity
+    int64_t ncolent = 0;
     int32_t *rowlen = nullptr;      // [nEnt] L(g) = row length of every row of entity g
     int32_t *selfpos = nullptr;     // [nEnt] position of the entity's own dofs in its column list
     // owned block range and value offsets

@@ -207,6 +207,13 @@ class AssemblyPlan:
             self._csr = (rowptr, colidx)
         return self._csr
 
+    def column_starts(self) -> torch.Tensor:
+        """First column (numbering in use) of every column entity of every entity's list."""
+        n = lib().pg_plan_num_column_entities(self._h)
+        out = torch.empty((max(n, 1),), dtype=torch.int32, device=self.elems.device)[:n]
+        check(lib().pg_plan_column_starts(self._h, ptr(out), stream_ptr()), "pg_plan_column_starts")
+        return out
+
     def dof_permutation(self) -> torch.Tensor:
         """perm[ref_dof] = index in the numbering in use."""
         perm = torch.empty((self.N,), dtype=torch.int32, device=self.elems.device)
@@ -244,17 +251,28 @@ class AssemblyPlan:
 class CSRMatrix:
     """Complex128 CSR block of owned rows [row_begin, row_begin+rows) x N columns."""
 
-    def __init__(self, rowptr, colidx, vals, N, row_begin=0):
+    def __init__(self, rowptr, colidx, vals, N, row_begin=0, plan=None, colstart=None):
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.N, self.row_begin = int(N), int(row_begin)
         self.rows = int(rowptr.numel() - 1)
         self.nnz = int(vals.numel())
+        # with the plan that produced vals (p = 2) MatMult uses the entity-blocked kernel: the plan's
+        # per-entity column lists replace colidx (17 B per nonzero instead of 20)
+        self.plan = plan if (plan is not None and plan.p == 2) else None
+        self.colstart = colstart  # None = the plan's own global column starts
 
     def mult(self, x: torch.Tensor, y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:
         """y = A x  (MatMult); x has N entries, y the owned rows.  With row_scale, y = row_scale .* (A x)
         (the Jacobi preconditioner applied in the SpMV epilogue)."""
         if y is None:
             y = torch.empty((self.rows,), dtype=torch.complex128, device=x.device)
+        if self.plan is not None:
+            check(
+                lib().pg_spmv_blocked(self.plan._h, ptr(self.colstart), ptr(self.vals), ptr(x), ptr(row_scale),
+                                      ptr(y), stream_ptr()),
+                "pg_spmv_blocked",
+            )
+            return y
         check(
             lib().pg_spmv_scaled(self.rows, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x),
                                  ptr(row_scale), ptr(y), stream_ptr()),

@@ -76,8 +76,16 @@ class DistContext:
                                     group=self.group)
         send_idx = wanted - lo  # rows of mine the others asked for, grouped by destination
         n = hi - lo
+        self._halo_ext, self._halo_lo, self._halo_hi = ext, lo, hi
         local = torch.where(outside, n + torch.searchsorted(ext, c), c - lo)
         return local.to(torch.int32), send_idx, send_splits, recv_splits
+
+    def remap_halo(self, cols: torch.Tensor) -> torch.Tensor:
+        """Same column map as build_halo for another index array (e.g. the entity column starts)."""
+        c = cols.to(torch.int64)
+        outside = (c < self._halo_lo) | (c >= self._halo_hi)
+        n = self._halo_hi - self._halo_lo
+        return torch.where(outside, n + torch.searchsorted(self._halo_ext, c), c - self._halo_lo).to(torch.int32)
 
     def exchange(self, x_local, send_idx, send_splits, recv_splits, sendbuf, xbuf):
         """xbuf = [x_local | halo]: pack, all_to_all over NCCL, unpack in place."""
@@ -119,12 +127,16 @@ class Operator:
                     self.halo_entries = next_
                     self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
                     self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
-                    self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin)
+                    cs = ctx.remap_halo(A.plan.column_starts()) if A.plan is not None else None
+                    self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=A.plan,
+                                            colstart=cs)
             if self.mode == "allgather":
                 self.colidx_local = ctx.remap_columns(A.colidx)
                 self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
                 self.full = torch.zeros((ctx.world * ctx.max_rows,), dtype=_C128, device=dev)
-                self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin)
+                cs = ctx.remap_columns(A.plan.column_starts()) if A.plan is not None else None
+                self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin,
+                                        plan=A.plan, colstart=cs)
         self.spmv_calls = 0
 
     def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
@@ -359,7 +371,8 @@ def bicgstab(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, 
     return SolveResult(x, maxit, hist, False, "maxit")
 
 
-def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None, check_every=10):
+def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None, check_every=10,
+         max_seconds=None):
     """Conjugate-orthogonal CG for the complex SYMMETRIC system (KSPCG with -ksp_cg_type symmetric):
     one SpMV, two unconjugated dots and three vector updates per iteration, no restart.  Jacobi enters
     symmetrically through z = D^-1 r; convergence is tested on the preconditioned residual like PETSc.
@@ -384,6 +397,8 @@ def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, moni
     hist = [bnorm]
     it = 0
     rho_i, rho_new_i = 0, 1
+    import time as _time
+    t_start = _time.time()
     while it < maxit:
         for _ in range(min(check_every, maxit - it)):
             op.matvec(p_, q)
@@ -407,6 +422,8 @@ def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, moni
             monitor(it, res)
         if res <= tol:
             return SolveResult(x, it, hist, True, "rtol")
+        if max_seconds is not None and _time.time() - t_start > max_seconds:
+            return SolveResult(x, it, hist, False, "time limit")
     return SolveResult(x, maxit, hist, False, "maxit")
 
 

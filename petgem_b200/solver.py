@@ -110,7 +110,7 @@ class Solver():
         rowptr, colidx = self.plan.csr()
         self.A = createParallelMatrix(self.total_num_dofs, self.total_num_dofs, self.nnz, run.get('cuda'))
         self.A.plan = self.plan
-        self.A.csr = CSRMatrix(rowptr, colidx, vals, self.plan.N)
+        self.A.csr = CSRMatrix(rowptr, colidx, vals, self.plan.N, plan=self.plan)
         self.A.perm = self.plan.dof_permutation() if order != 'reference' else None
 
         # ---- RHS ----

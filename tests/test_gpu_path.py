@@ -517,3 +517,86 @@ def test_bad_arguments_fail_loudly(topo):
         check(rc, "pg_element_matrices")
     with pytest.raises(PetgemB200Error):
         dv.AssemblyPlan(el, 1, order=np.zeros(el.nEdges, dtype=np.int32))  # not a permutation
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 6])
+def test_single_element_mesh(oracle, p):
+    """Smallest possible input: one tetrahedron (every entity has exactly one incident element)."""
+    from petgem_b200 import synthetic
+    from petgem_b200.device import AssemblyPlan, ElementData
+
+    nodes = np.array([[0.0, 0.0, 0.0], [2.0, 0.1, 0.0], [0.3, 1.5, 0.2], [0.1, 0.2, 1.1]])
+    elemsN = np.array([[2, 0, 3, 1]], dtype=np.int64)  # unsorted local order
+    X = nodes[elemsN[0]]
+    if np.linalg.det(X[1:] - X[0]) < 0:
+        elemsN[0, [2, 3]] = elemsN[0, [3, 2]]
+    tab = synthetic.mesh_tables(nodes, elemsN)
+    sigma = np.array([[0.3, 0.1]])
+    el = ElementData.from_mesh(nodes, elemsN, tab["elemsE"], tab["edgesNodes"], tab["elemsF"], tab["facesE"], sigma)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, p)
+    n = p * (p + 2) * (p + 3) // 2
+    assert plan.N == n and plan.nnz == n * n and plan.max_row_length == n
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    vals = plan.assemble(geo, code, omega, mu).cpu().numpy().reshape(n, n)
+    Ae = oracle.element_system(nodes[elemsN[0]], elemsN[0], tab["elemsE"][0], tab["edgesNodes"][tab["elemsE"][0]],
+                               tab["facesE"][tab["elemsF"][0]], sigma[0], p, omega, mu)
+    dofs, *_ = oracle.compute_connectivity_dofs(tab["elemsE"], tab["elemsF"], p)
+    ref = np.zeros((n, n), dtype=np.complex128)
+    ref[np.ix_(dofs[0], dofs[0])] = Ae
+    assert np.abs(vals - ref).max() <= REL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("order", ["reference", "locality"])
+def test_entity_blocked_spmv_equals_csr(topo, order):
+    """p=2 MatMult through the plan's per-entity column lists == the CSR kernel (also with the Jacobi
+    scaling epilogue, with Dirichlet rows, and on a row block of a partitioned matrix)."""
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, 2, order=order)
+    nE = topo["edgesNodes"].shape[0]
+    bd_entity = np.zeros(plan.nEnt, dtype=np.uint8)
+    bd_entity[topo["bEdges"]] = 1
+    bd_entity[nE + topo["bFaces"]] = 1
+    plan.set_dirichlet(bd_entity)
+    vals = plan.assemble(geo, code, omega, mu, apply_dirichlet=True)
+    rowptr, colidx = plan.csr()
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
+    d = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
+    Acsr = CSRMatrix(rowptr, colidx, vals, plan.N)
+    Ablk = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan)
+    assert Ablk.plan is not None and Acsr.plan is None
+    y0, y1 = Acsr.mult(x), Ablk.mult(x)
+    assert torch.linalg.vector_norm(y0 - y1) <= 1e-14 * torch.linalg.vector_norm(y0)
+    y0, y1 = Acsr.mult(x, row_scale=d), Ablk.mult(x, row_scale=d)
+    assert torch.linalg.vector_norm(y0 - y1) <= 1e-14 * torch.linalg.vector_norm(y0)
+    cs = plan.column_starts()
+    assert cs.numel() * 4 == plan.nnz  # one entry per 2x2 block
+    # owned row block
+    cut = plan.entity_aligned_row(plan.N // 3)
+    part = AssemblyPlan(el, 2, order=plan.order_host if plan.order_host is not None else "reference",
+                        row_range=(cut, plan.N))
+    part.set_dirichlet(bd_entity)
+    v2 = part.assemble(geo, code, omega, mu, apply_dirichlet=True)
+    rp2, ci2 = part.csr()
+    yb = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part).mult(x)
+    assert torch.linalg.vector_norm(yb - Acsr.mult(x)[cut:]) <= 1e-14 * torch.linalg.vector_norm(yb)
+
+
+def test_empty_inputs_are_accepted():
+    """Zero-size calls return PG_OK without touching memory (ragged partitions can own nothing)."""
+    from petgem_b200._lib import lib
+
+    L = lib()
+    assert L.pg_element_geometry(0, None, None, None, None, None, None, None, None, None) == 0
+    assert L.pg_element_matrices(0, 2, None, None, None, None, None, None) == -22  # both outputs null
+    assert L.pg_spmv(0, None, None, None, None, None, None) == 0
+    assert L.pg_zaxpy(0, None, None, None, None) == 0
+    assert L.pg_zmaxpy(5, 0, None, 1.0, None, 5, None, None) == 0
+    assert L.pg_zmdotc(5, 0, None, 5, None, None, None, None) == 0
+    assert L.pg_connectivity_dofs(0, 3, None, None, 0, 0, None, None) == 0
+    assert L.pg_zero_rows_columns(0, 0, None, None, None, 1.0, None, None) == 0
