@@ -478,7 +478,6 @@ def main():
 
     # ---- e2e through the public API with host buffers -----------------------------------------------
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in rows.items()}
-    h2d = sum(int(t.numel() * t.element_size()) for t in pinned.values())
     # the step's result read back by the host: ||A||_F^2 of the assembled block (a 16-byte metric, like a
     # loss), reduced on the device by pg_dznrm2sq
     from petgem_b200._lib import check, ptr, stream_ptr
@@ -486,10 +485,15 @@ def main():
     fro_dev = torch.zeros((1,), dtype=torch.complex128, device=dev)
     fro_work = torch.empty((lib().pg_reduce_workspace_bytes(1) // 16,), dtype=torch.complex128, device=dev)
 
+    # each rank needs (and copies) only the rows of the elements incident to its matrix rows
+    t0e, t1e = erange
+    dev_rows = {"nodes": el.nodes, "elemsN": el.elemsN, "elemsE": el.elemsE, "edgesNodes": el.edgesNodes,
+                "facesEdges": el.facesEdges, "elemsF": el.elemsF, "sigma": el.sigma}
+    h2d = sum(int(t[t0e:t1e].numel() * t.element_size()) for t in pinned.values())
+
     def e2e_step():
-        d = {k: t.to(dev, non_blocking=True) for k, t in pinned.items()}
-        el.nodes, el.elemsN, el.elemsE, el.edgesNodes = d["nodes"], d["elemsN"], d["elemsE"], d["edgesNodes"]
-        el.facesEdges, el.elemsF, el.sigma = d["facesEdges"], d["elemsF"], d["sigma"]
+        for k, t in pinned.items():
+            dev_rows[k][t0e:t1e].copy_(t[t0e:t1e], non_blocking=True)
         g, c = el.geometry(erange, out=gbuf)
         plan.assemble(g, c, OMEGA, MU, apply_dirichlet=True, diag=1.0, out=vals)
         check(lib().pg_dznrm2sq(plan.nnz, ptr(vals), ptr(fro_dev), ptr(fro_work), stream_ptr()), "pg_dznrm2sq")
@@ -507,6 +511,10 @@ def main():
     e2e_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / ksteps
     # the sampler ran over the timed assembly steps, the SpMV / Krylov section and the e2e steps
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1:  # bytes copied by all ranks together
+        t = torch.tensor([h2d], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        h2d = int(t.item())
     e2e = {"value": T / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms,
            "result": "squared Frobenius norm of the assembled matrix: %.17g" % fro_host[0].real.item()}
