@@ -344,7 +344,7 @@ def element_tables(p: int):
 # denominators that make the reference tensors integral (exact rationals: integrals of
 # integer-coefficient polynomials over the master tetrahedron); used by the p <= 2 kernel,
 # which keeps SK*DK and SM*DM as 16-bit integers in shared memory (pg_assemble.cu)
-INTEGER_SCALES = {1: (6, 120), 2: (120, 5040), 3: (5040, 362880)}
+INTEGER_SCALES = {1: (6, 120), 2: (120, 5040), 3: (5040, 362880), 4: (362880, 39916800), 5: (39916800, 6227020800)}
 
 
 def integer_tables(p: int):

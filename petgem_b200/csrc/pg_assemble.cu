@@ -32,11 +32,52 @@ struct AsmArgs {
     const double *geo;
     const uint32_t *code;
     const double *table;
+    const uint32_t *itable;    // p = 3..5: integer codes (numerator + 2^31), null otherwise
+    double inv_dk, inv_dm;     // 1/DK, 1/DM of the integer codes
     double mass_scale, diag;
     double2 *vals;
     int rc;         // rows per pass
     int bufstride;  // complex elements of shared tile per group
 };
+
+// integer denominators that make the reference tensors integral (basis.INTEGER_SCALES; asserted on the
+// host and in tests/test_host.py); numerators fit 32 bits up to p = 5
+__host__ __device__ inline double int_scale_k(int p) {
+    return p == 3 ? 5040.0 : p == 4 ? 362880.0 : p == 5 ? 39916800.0 : 0.0;
+}
+__host__ __device__ inline double int_scale_m(int p) {
+    return p == 3 ? 362880.0 : p == 4 ? 39916800.0 : p == 5 ? 6227020800.0 : 0.0;
+}
+
+__global__ void build_itable_kernel(int64_t npairs, int p, const double *__restrict__ table,
+                                    uint32_t *__restrict__ itable) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= npairs * 12) return;
+    const int c = (int)(i % 12);
+    const double v = table[i] * (c < 6 ? int_scale_k(p) : int_scale_m(p));
+    itable[i] = (uint32_t)((long long)rint(v) + 2147483648LL);
+}
+
+// 12-term contraction from integer codes: 2^52 + u has u in its low mantissa word, so
+// (2^52 + u) - (2^52 + 2^31) is the numerator exactly; half the table bytes of the fp64 form
+__device__ __forceinline__ void contract12i(const uint32_t *__restrict__ tab, const double *g, double &k, double &m) {
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(tab);
+    const uint4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(t4 + 2);
+    const double bias = 4503601774854144.0;  // 2^52 + 2^31
+    auto val = [&](unsigned u) { return __hiloint2double(0x43300000, (int)u) - bias; };
+    k = g[0] * val(a.x);
+    k = fma(g[1], val(a.y), k);
+    k = fma(g[2], val(a.z), k);
+    k = fma(g[3], val(a.w), k);
+    k = fma(g[4], val(b.x), k);
+    k = fma(g[5], val(b.y), k);
+    m = g[6] * val(b.z);
+    m = fma(g[7], val(b.w), m);
+    m = fma(g[8], val(c.x), m);
+    m = fma(g[9], val(c.y), m);
+    m = fma(g[10], val(c.z), m);
+    m = fma(g[11], val(c.w), m);
+}
 
 template <int G>
 __device__ __forceinline__ void group_sync(unsigned mask) {
@@ -106,7 +147,13 @@ __global__ void __launch_bounds__(THREADS) assemble_kernel(const AsmArgs a) {
                     const int Jx = expanded_of_slot<P>(rslot, d0 + dd, cd, s1);
                     const int Kx = expanded_of_slot<P>(ks, kd, cd, s2);
                     double kk, mm;
-                    contract12(a.table + ((int64_t)Jx * O::nexp + Kx) * 12, gf, kk, mm);
+                    if (a.itable) {
+                        contract12i(a.itable + ((int64_t)Jx * O::nexp + Kx) * 12, gf, kk, mm);
+                        kk *= a.inv_dk;
+                        mm *= a.inv_dm;
+                    } else {
+                        contract12(a.table + ((int64_t)Jx * O::nexp + Kx) * 12, gf, kk, mm);
+                    }
                     const double s = s1 * s2;
                     double2 *dst = buf + dd * L + rec->slotpos[ks] + kd;
                     double2 cur = *dst;
@@ -576,6 +623,21 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
     a.hdr = pl->hdr;
     a.bd_entity = apply_dirichlet ? pl->bd_entity : nullptr;
     a.geo = geo, a.code = code, a.table = table;
+    a.itable = nullptr, a.inv_dk = a.inv_dm = 0.0;
+    if (pl->p >= 3 && pl->p <= 5) {
+        // integer codes of the table (lazily built, cached in the plan for this table pointer)
+        const int64_t npairs = (int64_t)pg_nexp(pl->p) * pg_nexp(pl->p);
+        if (pl->itable_src != table) {
+            if (!pl->itable) PG_CUDA_OK(cudaMalloc((void **)&pl->itable, npairs * 12 * sizeof(uint32_t)));
+            build_itable_kernel<<<(unsigned)((npairs * 12 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                npairs, pl->p, table, pl->itable);
+            PG_LAUNCH_OK();
+            pl->itable_src = table;
+        }
+        a.itable = pl->itable;
+        a.inv_dk = 1.0 / int_scale_k(pl->p);
+        a.inv_dm = 1.0 / int_scale_m(pl->p);
+    }
     a.mass_scale = mass_scale, a.diag = diag;
     a.vals = reinterpret_cast<double2 *>(vals);
     a.rc = 1, a.bufstride = 0;

@@ -418,6 +418,7 @@ void pg_plan_destroy(pg_plan *pl) {
     cudaFree(pl->selfpos);
     cudaFree(pl->valoff);
     cudaFree(pl->hdr);
+    cudaFree(pl->itable);
     cudaFree(pl->bd_entity);
     delete pl;
 }

@@ -62,4 +62,7 @@ struct pg_plan {
     int64_t elem_begin = 0, elem_end = 0;  // range of elements incident to owned rows
     int max_rowlen = 0;
     uint8_t *bd_entity = nullptr;   // [nEnt] own copy, set by pg_plan_set_dirichlet
+    // p = 3..5: exact integer codes of the reference tensors (built lazily by pg_assemble from `table`)
+    mutable uint32_t *itable = nullptr;      // [nexp*nexp][12] numerator + 2^31
+    mutable const double *itable_src = nullptr;
 };

@@ -59,8 +59,8 @@ class Solver():
         mode = inputSetup.model.get('mode')
         if mode == 'csem':
             self.boundaries = readPetscVector(out_dir + '/boundaries.dat')
-            if parEnv.rank == 0:
-                self.source_data = readPetscVector(out_dir + '/source.dat')
+            # every rank keeps replicated b/x vectors, so every rank reads the (tiny) source record
+            self.source_data = readPetscVector(out_dir + '/source.dat')
         elif mode == 'mt':
             self.boundaries = readPetscMatrix(out_dir + '/boundaryElements.dat')
 
@@ -105,12 +105,21 @@ class Solver():
         if self.plan.N != self.total_num_dofs:
             Print.master('     Number of DOFs is not consistent')
             exit(-1)
-        geo, code = self.elems.geometry()
+        self.row_begins = [0]
+        if parEnv.num_proc > 1:
+            # PETSc-style contiguous row blocks (aligned to entities): each rank assembles the rows it owns
+            N, world = self.plan.N, parEnv.num_proc
+            self.row_begins = [0] + [self.plan.entity_aligned_row(N * r // world) for r in range(1, world)]
+            ends = self.row_begins[1:] + [N]
+            order_host = self.plan.order_host if self.plan.order_host is not None else 'reference'
+            self.plan = AssemblyPlan(self.elems, basis_order, order=order_host,
+                                     row_range=(self.row_begins[parEnv.rank], ends[parEnv.rank]))
+        geo, code = self.elems.geometry(self.plan.element_range)
         vals = self.plan.assemble(geo, code, omega, mu)
         rowptr, colidx = self.plan.csr()
         self.A = createParallelMatrix(self.total_num_dofs, self.total_num_dofs, self.nnz, run.get('cuda'))
         self.A.plan = self.plan
-        self.A.csr = CSRMatrix(rowptr, colidx, vals, self.plan.N, plan=self.plan)
+        self.A.csr = CSRMatrix(rowptr, colidx, vals, self.plan.N, self.plan.row_begin, plan=self.plan)
         self.A.perm = self.plan.dof_permutation() if order != 'reference' else None
 
         # ---- RHS ----
@@ -125,7 +134,7 @@ class Solver():
             moment = src.get('current') * src.get('length')
             field = rot[0] * np.array([moment, 0., 0.]) + rot[1] * np.array([0., moment, 0.]) \
                 + rot[2] * np.array([0., 0., moment])
-            if parEnv.rank == 0:
+            if True:  # replicated vectors: every rank adds the same source contribution
                 sd = self.source_data.getArray().real
                 nodesEle = sd[0:4].astype(np.int64)
                 coordEle = sd[4:16].reshape(4, 3)
@@ -177,7 +186,10 @@ class Solver():
 
         Timers()["Solver"].start()
         self.ksp_results = []
+        parEnv = MPIEnvironment()
         perm = self.A.perm.to(torch.int64) if self.A.perm is not None else None
+        ctx = krylov.DistContext(self.row_begins, self.plan.N) if parEnv.num_proc > 1 else None
+        lo, hi = self.plan.row_begin, self.plan.row_begin + self.plan.local_rows
         for i in np.arange(num_polarizations):
             b = self.b[i].t
             if perm is not None:
@@ -185,12 +197,19 @@ class Solver():
                 bi[perm] = b
             else:
                 bi = b
-            res = krylov.solve(self.A.csr, bi, self.petsc_options)      # ksp.solve(b, x), solver.py:589
+            res = krylov.solve(self.A.csr, bi[lo:hi].contiguous(), self.petsc_options, ctx=ctx)  # solver.py:589
             self.ksp_results.append(res)
-            self.x[i].t.copy_(res.x[perm] if perm is not None else res.x)
+            xi = res.x
+            if ctx is not None:  # collect the owned blocks into the replicated solution vector
+                send = torch.zeros((ctx.max_rows,), dtype=torch.complex128, device=xi.device)
+                full = torch.zeros((ctx.world * ctx.max_rows,), dtype=torch.complex128, device=xi.device)
+                ctx.gather(xi, send, full)
+                xi = torch.cat([full[r * ctx.max_rows:r * ctx.max_rows + ctx.sizes[r]] for r in range(ctx.world)])
+            self.x[i].t.copy_(xi[perm] if perm is not None else xi)
             if not res.converged:
                 Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
-            writePetscVector(out_dir + '/x' + str(i) + '.dat', self.x[i])
+            if parEnv.rank == 0:
+                writePetscVector(out_dir + '/x' + str(i) + '.dat', self.x[i])
         torch.cuda.synchronize()
         Timers()["Solver"].stop()
         return

@@ -135,6 +135,31 @@ def test_cpu_matrix_type_fails_loudly():
 
 
 @pytest.mark.gpu
+def test_kernel_cli_two_ranks_match_one(tmp_path, topo):
+    """torchrun -n 2 kernel.py (row blocks over 2 GPUs, NCCL halo + allreduce) gives the same receiver
+    fields as the single-GPU run (p=2)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fields = []
+    for world in (1, 2):
+        d = tmp_path / ("w%d" % world)
+        d.mkdir()
+        params, opts = make_case(d, topo, nord=2)
+        open(opts, "w").write("-ksp_type cg\n-ksp_cg_type symmetric\n-pc_type jacobi\n-ksp_rtol 1e-11\n-ksp_max_it 40000\n")
+        cmd = [sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params]
+        if world > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                   "--master-addr", "127.0.0.1", "--master-port", "29533"] + cmd[1:]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+        fields.append(np.load(str(d / "out" / "fields.npz"))["fields_0"])
+    scale = np.abs(fields[0][:, :3]).max()
+    assert np.abs(fields[0][:, :3] - fields[1][:, :3]).max() <= 1e-6 * scale
+
+
+@pytest.mark.gpu
 def test_kernel_cli_end_to_end(tmp_path, topo, oracle):
     """python3 kernel.py -options_file petsc.opts params.yaml on the reference's test mesh (case1
     physics, p=1): receiver E-fields within 1e-6 of a direct solve of the oracle's system."""
