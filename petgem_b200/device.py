@@ -251,14 +251,19 @@ class AssemblyPlan:
 class CSRMatrix:
     """Complex128 CSR block of owned rows [row_begin, row_begin+rows) x N columns."""
 
-    def __init__(self, rowptr, colidx, vals, N, row_begin=0, plan=None, colstart=None):
+    def __init__(self, rowptr, colidx, vals, N, row_begin=0, plan=None, colstart=None, blocked=None):
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.N, self.row_begin = int(N), int(row_begin)
         self.rows = int(rowptr.numel() - 1)
         self.nnz = int(vals.numel())
-        # with the plan that produced vals (p = 2) MatMult uses the entity-blocked kernel: the plan's
-        # per-entity column lists replace colidx (17 B per nonzero instead of 20)
-        self.plan = plan if (plan is not None and plan.p == 2) else None
+        # with the plan that produced vals (p = 2) MatMult can use the entity-blocked kernel: the plan's
+        # per-entity column lists replace colidx (17 B per nonzero instead of 20).  Measured on B200
+        # (tools/spmv_bench.py): +5 % at 1.6 M tets, -3 % at 5 M tets against the CSR kernel -- the SpMV is
+        # latency- rather than byte-bound there -- so it is opt-in (blocked=True or PG_SPMV_BLOCKED=1).
+        import os
+        if blocked is None:
+            blocked = os.environ.get("PG_SPMV_BLOCKED", "0") == "1"
+        self.plan = plan if (blocked and plan is not None and plan.p == 2) else None
         self.colstart = colstart  # None = the plan's own global column starts
 
     def mult(self, x: torch.Tensor, y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:

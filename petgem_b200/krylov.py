@@ -129,14 +129,14 @@ class Operator:
                     self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
                     cs = ctx.remap_halo(A.plan.column_starts()) if A.plan is not None else None
                     self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=A.plan,
-                                            colstart=cs)
+                                            colstart=cs, blocked=A.plan is not None)
             if self.mode == "allgather":
                 self.colidx_local = ctx.remap_columns(A.colidx)
                 self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
                 self.full = torch.zeros((ctx.world * ctx.max_rows,), dtype=_C128, device=dev)
                 cs = ctx.remap_columns(A.plan.column_starts()) if A.plan is not None else None
                 self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin,
-                                        plan=A.plan, colstart=cs)
+                                        plan=A.plan, colstart=cs, blocked=A.plan is not None)
         self.spmv_calls = 0
 
     def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:

@@ -568,7 +568,7 @@ def test_entity_blocked_spmv_equals_csr(topo, order):
     x = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
     d = torch.randn(plan.N, dtype=torch.complex128, generator=gen).to(vals.device)
     Acsr = CSRMatrix(rowptr, colidx, vals, plan.N)
-    Ablk = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan)
+    Ablk = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan, blocked=True)
     assert Ablk.plan is not None and Acsr.plan is None
     y0, y1 = Acsr.mult(x), Ablk.mult(x)
     assert torch.linalg.vector_norm(y0 - y1) <= 1e-14 * torch.linalg.vector_norm(y0)
@@ -583,7 +583,7 @@ def test_entity_blocked_spmv_equals_csr(topo, order):
     part.set_dirichlet(bd_entity)
     v2 = part.assemble(geo, code, omega, mu, apply_dirichlet=True)
     rp2, ci2 = part.csr()
-    yb = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part).mult(x)
+    yb = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part, blocked=True).mult(x)
     assert torch.linalg.vector_norm(yb - Acsr.mult(x)[cut:]) <= 1e-14 * torch.linalg.vector_norm(yb)
 
 
