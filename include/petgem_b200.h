@@ -116,6 +116,13 @@ void pg_plan_destroy(pg_plan *plan);
 int pg_plan_locality_order(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
                            int64_t nFaces, int32_t *ent_order_host, void *stream);
 
+/* same, but "first" is taken in the caller's element traversal: elem_rank [T] i32 (device) = position of
+ * each element in that traversal (e.g. a Morton / Hilbert curve through the centroids), NULL = element id.
+ * A space-filling traversal keeps the x entries a row touches close together in memory (SpMV re-fetches)
+ * and makes contiguous row blocks compact 3-D chunks (multi-GPU halo). */
+int pg_plan_ranked_order(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
+                         int64_t nFaces, const int32_t *elem_rank, int32_t *ent_order_host, void *stream);
+
 int64_t pg_plan_num_dofs(const pg_plan *plan);      /* N (global) */
 int64_t pg_plan_num_entities(const pg_plan *plan);  /* entities that carry dofs */
 int64_t pg_plan_local_rows(const pg_plan *plan);    /* row_end - row_begin */

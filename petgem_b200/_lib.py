@@ -66,6 +66,7 @@ SIGNATURES = {
     "pg_plan_create": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _i64, _i64, C.POINTER(_p), _p]),
     "pg_plan_destroy": (None, [_p]),
     "pg_plan_locality_order": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _p]),
+    "pg_plan_ranked_order": (C.c_int, [_i64, _i32, _p, _p, _i64, _i64, _p, _p, _p]),
     "pg_plan_num_dofs": (_i64, [_p]),
     "pg_plan_num_entities": (_i64, [_p]),
     "pg_plan_local_rows": (_i64, [_p]),

@@ -44,12 +44,24 @@ __global__ void invert_order_kernel(int64_t n, const int32_t *__restrict__ order
 }
 
 // first incidence value of each entity (element-major locality key)
-__global__ void first_incidence_kernel(int64_t nEnt, const int32_t *__restrict__ inc_ptr,
-                                       const int32_t *__restrict__ sorted_vals, int32_t *__restrict__ key) {
+__global__ void first_incidence_kernel(int64_t nEnt, int nslots, const int32_t *__restrict__ inc_ptr,
+                                       const int32_t *__restrict__ sorted_vals,
+                                       const int32_t *__restrict__ elem_rank, int32_t *__restrict__ key) {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= nEnt) return;
     int32_t a = inc_ptr[g], b = inc_ptr[g + 1];
-    key[g] = (b > a) ? sorted_vals[a] : 2147483647;
+    int32_t k = 2147483647;
+    if (b > a) {
+        if (!elem_rank) {
+            k = sorted_vals[a];  // incidences are sorted by element: the first one is the smallest
+        } else {                 // entity key = earliest incident element in the caller's traversal
+            for (int32_t i = a; i < b; ++i) {
+                const int32_t v = sorted_vals[i], t = v / nslots;
+                k = min(k, elem_rank[t] * nslots + (v - t * nslots));
+            }
+        }
+    }
+    key[g] = k;
 }
 
 // PASS 0: count unique column entities and the row length; PASS 1: fill lists and records.
@@ -425,6 +437,11 @@ void pg_plan_destroy(pg_plan *pl) {
 
 int pg_plan_locality_order(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nE, int64_t nF,
                            int32_t *ent_order_host, void *stream) {
+    return pg_plan_ranked_order(T, p, elemsE, elemsF, nE, nF, nullptr, ent_order_host, stream);
+}
+
+int pg_plan_ranked_order(int64_t T, int p, const int32_t *elemsE, const int32_t *elemsF, int64_t nE, int64_t nF,
+                         const int32_t *elem_rank, int32_t *ent_order_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int64_t nEnt, N;
     int rc = check_sizes(T, p, nE, nF, nEnt, N);
@@ -441,8 +458,8 @@ int pg_plan_locality_order(int64_t T, int p, const int32_t *elemsE, const int32_
     PG_CUDA_OK(cudaMalloc(&ids.p, nEnt * 4));
     PG_CUDA_OK(cudaMalloc(&ids_out.p, nEnt * 4));
     const unsigned gb = (unsigned)((nEnt + 255) / 256);
-    first_incidence_kernel<<<gb, 256, 0, st>>>(nEnt, inc_ptr.as<int32_t>(), sorted_vals.as<int32_t>(),
-                                               key.as<int32_t>());
+    first_incidence_kernel<<<gb, 256, 0, st>>>(nEnt, nslots_of(p), inc_ptr.as<int32_t>(), sorted_vals.as<int32_t>(),
+                                               elem_rank, key.as<int32_t>());
     PG_LAUNCH_OK();
     iota_kernel<<<gb, 256, 0, st>>>(nEnt, ids.as<int32_t>());
     PG_LAUNCH_OK();

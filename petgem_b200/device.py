@@ -144,10 +144,34 @@ def element_systems(p: int, geo: torch.Tensor, code: torch.Tensor, omega: float,
     return Ae
 
 
+def morton_element_rank(nodes12: np.ndarray) -> np.ndarray:
+    """Position of every element along a Morton (Z-order) curve through the element centroids.
+    nodes12: [T,12] per-element vertex coordinates (the nodes.dat rows) -> int32 [T]."""
+    X = np.asarray(nodes12, dtype=np.float64).reshape(-1, 4, 3).mean(axis=1)
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    q = np.minimum(((X - lo) / np.maximum(hi - lo, 1e-300) * 1024.0).astype(np.int64), 1023)  # 10 bits per axis
+
+    def spread(v):  # 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    order = np.argsort(key, kind="stable")
+    rank = np.empty(order.size, dtype=np.int32)
+    rank[order] = np.arange(order.size, dtype=np.int32)
+    return rank
+
+
 class AssemblyPlan:
     """Symbolic phase (pattern, incidence lists, slot positions) for one mesh and order."""
 
-    def __init__(self, elems: ElementData, p: int, order="reference", row_range=None):
+    def __init__(self, elems: ElementData, p: int, order="reference", row_range=None, elem_rank=None):
+        """order: 'reference' (PETGEM numbering), 'locality' (element-major: entities by first incident
+        element; with elem_rank [T] = position of each element in a space-filling traversal, by first
+        incident element along that curve -- see morton_element_rank), or an explicit entity order."""
         self.elems, self.p = elems, p
         self.n = basis.ndof_element(p)
         nEnt = elems.nEdges + (elems.nFaces if p >= 2 else 0) + (elems.T if p >= 3 else 0)
@@ -157,10 +181,13 @@ class AssemblyPlan:
                 order_host = None
             elif order == "locality":
                 order_host = np.empty(nEnt, dtype=np.int32)
+                rank_dev = None
+                if elem_rank is not None:
+                    rank_dev = torch.as_tensor(np.ascontiguousarray(elem_rank, dtype=np.int32)).to(elems.device)
                 check(
-                    lib().pg_plan_locality_order(elems.T, p, ptr(elems.elemsE), ptr(elems.elemsF), elems.nEdges,
-                                                 elems.nFaces, ptr(order_host), stream_ptr()),
-                    "pg_plan_locality_order",
+                    lib().pg_plan_ranked_order(elems.T, p, ptr(elems.elemsE), ptr(elems.elemsF), elems.nEdges,
+                                               elems.nFaces, ptr(rank_dev), ptr(order_host), stream_ptr()),
+                    "pg_plan_ranked_order",
                 )
             else:
                 raise ValueError("order must be 'reference', 'locality' or an int32 array")

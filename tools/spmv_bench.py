@@ -16,20 +16,32 @@ from petgem_b200.device import AssemblyPlan, CSRMatrix, ElementData  # noqa: E40
 ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=64)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--morton", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 tab = bench.build_case(args.m, 2)
 rows = bench.host_rows(tab)
 el = ElementData(rows["nodes"], rows["elemsN"], rows["elemsE"], rows["edgesNodes"], rows["facesEdges"], rows["elemsF"],
                  rows["sigma"], tab["nEdges"], tab["nFaces"], device=dev)
-plan = AssemblyPlan(el, 2, order="locality")
+from petgem_b200.device import morton_element_rank  # noqa: E402
+rank = morton_element_rank(rows["nodes"]) if args.morton else None
+plan = AssemblyPlan(el, 2, order="locality", elem_rank=rank)
 plan.set_dirichlet(bench.bd_entities(tab, 2, plan.nEnt))
 g, c = el.geometry()
 vals = plan.assemble(g, c, bench.OMEGA, bench.MU, apply_dirichlet=True)
+torch.cuda.synchronize()
+ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ea.record()
+for _ in range(5):
+    plan.assemble(g, c, bench.OMEGA, bench.MU, apply_dirichlet=True, out=vals)
+eb.record()
+torch.cuda.synchronize()
+asm_ms = ea.elapsed_time(eb) / 5
 rowptr, colidx = plan.csr()
 x = torch.randn(plan.N, dtype=torch.complex128, device=dev)
 out = {}
-for name, A in (("csr", CSRMatrix(rowptr, colidx, vals, plan.N)), ("blocked", CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan))):
+for name, A in (("csr", CSRMatrix(rowptr, colidx, vals, plan.N)),
+                ("blocked", CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan, blocked=True))):
     y = A.mult(x)
     for _ in range(3):
         A.mult(x, y)
@@ -42,5 +54,6 @@ for name, A in (("csr", CSRMatrix(rowptr, colidx, vals, plan.N)), ("blocked", CS
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     out[name] = (ms, (20.0 * plan.nnz + 40.0 * plan.N) / ms / 1e6)
-print("hints=%s m=%d nnz=%d :" % (os.environ.get("PG_SPMV_HINTS", "0"), args.m, plan.nnz),
+print("hints=%s morton=%d m=%d nnz=%d assemble %.3f ms:" % (os.environ.get("PG_SPMV_HINTS", "1"), args.morton, args.m,
+                                                            plan.nnz, asm_ms),
       " ".join("%s %.3f ms %.0f GB/s" % (k, v[0], v[1]) for k, v in out.items()))
