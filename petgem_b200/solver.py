@@ -134,20 +134,20 @@ class Solver():
             moment = src.get('current') * src.get('length')
             field = rot[0] * np.array([moment, 0., 0.]) + rot[1] * np.array([0., moment, 0.]) \
                 + rot[2] * np.array([0., 0., moment])
-            if True:  # replicated vectors: every rank adds the same source contribution
-                sd = self.source_data.getArray().real
-                nodesEle = sd[0:4].astype(np.int64)
-                coordEle = sd[4:16].reshape(4, 3)
-                edgesFace = sd[20:32].astype(np.int64).reshape(4, 3)
-                edgesEle = sd[32:38].astype(np.int64)
-                edgesNodesEle = sd[38:50].astype(np.int64).reshape(6, 2)
-                dofsSource = sd[50:].astype(np.int64)
-                jacobian, invjacobian = hvfem.computeJacobian(coordEle)
-                eo, fo = hvfem.computeElementOrientation(edgesEle, nodesEle, edgesNodesEle, edgesFace)
-                XiEtaZeta = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, position)
-                basis, _ = hvfem.computeBasisFunctions(eo, fo, jacobian, invjacobian, basis_order, XiEtaZeta)
-                rhs_contribution = np.matmul(field, basis[:, :, 0]) * Const
-                self.b[0].setValues(dofsSource, rhs_contribution, addv=True)
+            # b and x are replicated on every rank (the reference inserts on rank 0 into a distributed Vec)
+            sd = self.source_data.getArray().real
+            nodesEle = sd[0:4].astype(np.int64)
+            coordEle = sd[4:16].reshape(4, 3)
+            edgesFace = sd[20:32].astype(np.int64).reshape(4, 3)
+            edgesEle = sd[32:38].astype(np.int64)
+            edgesNodesEle = sd[38:50].astype(np.int64).reshape(6, 2)
+            dofsSource = sd[50:].astype(np.int64)
+            jacobian, invjacobian = hvfem.computeJacobian(coordEle)
+            eo, fo = hvfem.computeElementOrientation(edgesEle, nodesEle, edgesNodesEle, edgesFace)
+            XiEtaZeta = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, position)
+            basis, _ = hvfem.computeBasisFunctions(eo, fo, jacobian, invjacobian, basis_order, XiEtaZeta)
+            rhs_contribution = np.matmul(field, basis[:, :, 0]) * Const
+            self.b[0].setValues(dofsSource, rhs_contribution, addv=True)
         elif mode == 'mt':
             Print.master('     MT boundary right-hand side (solver.py:318-512) is outside the B200 hot path: '
                          'assemble b with the reference and pass it through b{i}.dat')
