@@ -377,13 +377,14 @@ __global__ void __launch_bounds__(512, 1) assemble_small_kernel(const AsmArgs a)
     constexpr int G = S::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: integer table, SoA: A [NENT] x 16 B (K0..K5, M0, M1) | B [NENT] x 8 B (M2..M5) |
-    //         staged records [groups][MC+1] (the +1 staggers the groups over the banks) |
+    //         staged records [groups][2 (MC+1) + 1] (odd number of 32-byte records per group: the four
+    //         groups of a warp read their records from disjoint banks) |
     //         tiles [groups][R*L] complex
     uint4 *s_tabA = reinterpret_cast<uint4 *>(smem_raw);
     uint2 *s_tabB = reinterpret_cast<uint2 *>(s_tabA + S::NENT);
     const int groups = blockDim.x / G;
     IncRecord *s_rec = reinterpret_cast<IncRecord *>(s_tabB + S::NENT);
-    EntHdr *s_hdr = reinterpret_cast<EntHdr *>(s_rec + groups * 2 * (S::MC + 1));  // 3 headers per group
+    EntHdr *s_hdr = reinterpret_cast<EntHdr *>(s_rec + groups * (2 * (S::MC + 1) + 1));  // 3 headers per group
     double2 *s_buf = reinterpret_cast<double2 *>(s_hdr + groups * 3);
 
     {   // fill the integer table from the general fp64 table (L2 resident)
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(512, 1) assemble_small_kernel(const AsmArgs a)
     const int grp = threadIdx.x / G;
     const int lane = threadIdx.x % G;
     const unsigned mask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
-    IncRecord *rec = s_rec + grp * 2 * (S::MC + 1);  // two staging buffers (double buffered)
+    IncRecord *rec = s_rec + grp * (2 * (S::MC + 1) + 1);  // two staging buffers (double buffered)
 
     SmallCtx<P> cx;
     cx.tabA = s_tabA;
@@ -555,7 +556,7 @@ static int launch_assemble_small(const pg_plan *pl, AsmArgs a, cudaStream_t st) 
     using S = Small<P>;
     const int L = pl->max_rowlen;
     const size_t table_bytes = (size_t)S::NENT * 24;
-    const size_t per_group = 2 * (S::MC + 1) * sizeof(IncRecord) + 3 * sizeof(EntHdr) + (size_t)S::R * L * 16;
+    const size_t per_group = (2 * (S::MC + 1) + 1) * sizeof(IncRecord) + 3 * sizeof(EntHdr) + (size_t)S::R * L * 16;
     const size_t budget = 227 * 1024 - 1024;
     PG_REQUIRE(table_bytes + 4 * per_group <= budget, PG_ERANGE,
                "pg_assemble: row length %d does not fit in shared memory", L);
