@@ -32,7 +32,7 @@ struct AsmArgs {
     const double *geo;
     const uint32_t *code;
     const double *table;
-    const uint32_t *itable;    // p = 3..5: integer codes (numerator + 2^31), null otherwise
+    const int32_t *itable;     // p = 3..5: exact integer numerators of the table, null otherwise
     double inv_dk, inv_dm;     // 1/DK, 1/DM of the integer codes
     double mass_scale, diag;
     double2 *vals;
@@ -50,122 +50,202 @@ __host__ __device__ inline double int_scale_m(int p) {
 }
 
 __global__ void build_itable_kernel(int64_t npairs, int p, const double *__restrict__ table,
-                                    uint32_t *__restrict__ itable) {
+                                    int32_t *__restrict__ itable) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= npairs * 12) return;
     const int c = (int)(i % 12);
     const double v = table[i] * (c < 6 ? int_scale_k(p) : int_scale_m(p));
-    itable[i] = (uint32_t)((long long)rint(v) + 2147483648LL);
+    itable[i] = (int32_t)rint(v);
 }
 
-// 12-term contraction from integer codes: 2^52 + u has u in its low mantissa word, so
-// (2^52 + u) - (2^52 + 2^31) is the numerator exactly; half the table bytes of the fp64 form
-__device__ __forceinline__ void contract12i(const uint32_t *__restrict__ tab, const double *g, double &k, double &m) {
-    const uint4 *t4 = reinterpret_cast<const uint4 *>(tab);
-    const uint4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(t4 + 2);
-    const double bias = 4503601774854144.0;  // 2^52 + 2^31
-    auto val = [&](unsigned u) { return __hiloint2double(0x43300000, (int)u) - bias; };
-    k = g[0] * val(a.x);
-    k = fma(g[1], val(a.y), k);
-    k = fma(g[2], val(a.z), k);
-    k = fma(g[3], val(a.w), k);
-    k = fma(g[4], val(b.x), k);
-    k = fma(g[5], val(b.y), k);
-    m = g[6] * val(b.z);
-    m = fma(g[7], val(b.w), m);
-    m = fma(g[8], val(c.x), m);
-    m = fma(g[9], val(c.y), m);
-    m = fma(g[10], val(c.z), m);
-    m = fma(g[11], val(c.w), m);
-}
+// ---------------------------------------------------------------------------
+// p >= 3: one warp per entity, table in L2
+//
+// * Lane l owns the local columns k = l, l + 32, ... (NC = ceil(n / 32) of them): their slot
+//   and index inside the slot never change, and per incident element the expanded function
+//   index, the orientation sign and the position in the entity's column list are worked out
+//   once per column, not once per entry.
+// * The table entry of a (row function, column function) pair is 12 exact integers (48 bytes,
+//   p <= 5) widened with I2F, or 12 doubles (p = 6, numerators exceed 32 bits); all loads of a
+//   batch of columns are issued before the first contraction.
+// * The entity's rows are built in a shared tile of `bufstride` complex entries: as many rows
+//   per pass as fit (all of them for most entities), records staged MC at a time.
+// ---------------------------------------------------------------------------
+template <int P>
+struct Gen {
+    static constexpr int n = Ord<P>::n;
+    static constexpr int NC = (n + 31) / 32;        // columns per lane
+    static constexpr int JB = NC < 3 ? NC : 3;      // columns per load batch
+    static constexpr int MC = 8;                    // records staged per chunk
+    static constexpr int GROUPS = 4;                // warps per block, one entity each
+};
 
-template <int G>
-__device__ __forceinline__ void group_sync(unsigned mask) {
-    if (G == 32) __syncwarp(); else __syncwarp(mask);
-}
+template <bool ITAB>
+struct TabEntry;
+template <>
+struct TabEntry<true> {  // exact integer numerators
+    int4 w[3];
+    __device__ __forceinline__ void load(const AsmArgs &a, int64_t e) {
+        const int4 *q = reinterpret_cast<const int4 *>(a.itable) + e * 3;
+        w[0] = __ldg(q), w[1] = __ldg(q + 1), w[2] = __ldg(q + 2);
+    }
+    __device__ __forceinline__ void contract(const double (&g)[12], double &k, double &m) const {
+        k = g[0] * (double)w[0].x;
+        k = fma(g[1], (double)w[0].y, k);
+        k = fma(g[2], (double)w[0].z, k);
+        k = fma(g[3], (double)w[0].w, k);
+        k = fma(g[4], (double)w[1].x, k);
+        k = fma(g[5], (double)w[1].y, k);
+        m = g[6] * (double)w[1].z;
+        m = fma(g[7], (double)w[1].w, m);
+        m = fma(g[8], (double)w[2].x, m);
+        m = fma(g[9], (double)w[2].y, m);
+        m = fma(g[10], (double)w[2].z, m);
+        m = fma(g[11], (double)w[2].w, m);
+    }
+};
+template <>
+struct TabEntry<false> {  // fp64 table
+    double2 w[6];
+    __device__ __forceinline__ void load(const AsmArgs &a, int64_t e) {
+        const double2 *q = reinterpret_cast<const double2 *>(a.table) + e * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i);
+    }
+    __device__ __forceinline__ void contract(const double (&g)[12], double &k, double &m) const {
+        k = g[0] * w[0].x;
+        k = fma(g[1], w[0].y, k);
+        k = fma(g[2], w[1].x, k);
+        k = fma(g[3], w[1].y, k);
+        k = fma(g[4], w[2].x, k);
+        k = fma(g[5], w[2].y, k);
+        m = g[6] * w[3].x;
+        m = fma(g[7], w[3].y, m);
+        m = fma(g[8], w[4].x, m);
+        m = fma(g[9], w[4].y, m);
+        m = fma(g[10], w[5].x, m);
+        m = fma(g[11], w[5].y, m);
+    }
+};
 
-template <int P, int G, int THREADS>
-__global__ void __launch_bounds__(THREADS) assemble_kernel(const AsmArgs a) {
+template <int P, bool ITAB>
+__global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
     using O = Ord<P>;
-    constexpr int GROUPS = THREADS / G;
+    using S = Gen<P>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IncRecord *s_rec = reinterpret_cast<IncRecord *>(smem_raw);
-    double2 *s_buf = reinterpret_cast<double2 *>(smem_raw + GROUPS * sizeof(IncRecord));
+    double2 *s_buf = reinterpret_cast<double2 *>(s_rec + S::GROUPS * S::MC);
 
-    const int grp = threadIdx.x / G;
-    const int lane = threadIdx.x % G;
-    const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const int grp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     double2 *buf = s_buf + (size_t)grp * a.bufstride;
-    IncRecord *rec = s_rec + grp;
+    IncRecord *rec = s_rec + grp * S::MC;
 
-    const int64_t ngroups = (int64_t)gridDim.x * GROUPS;
-    for (int64_t b = a.b0 + blockIdx.x * (int64_t)GROUPS + grp; b < a.b1; b += ngroups) {
-        const int32_t g = __ldg(a.ent_order + b);
-        const int r = (int)(__ldg(a.row_base + b + 1) - __ldg(a.row_base + b));
-        const int L = __ldg(a.rowlen + g);
-        double2 *out = a.vals + __ldg(a.valoff + (b - a.b0));
+    int cks[S::NC], ckd[S::NC];  // slot and index inside the slot of the lane's columns (-1: none)
+#pragma unroll
+    for (int j = 0; j < S::NC; ++j) {
+        const int k = lane + 32 * j;
+        slot_of_local<P>(k < S::n ? k : 0, cks[j], ckd[j]);
+        if (k >= S::n) cks[j] = -1;
+    }
+    const double scK = ITAB ? a.inv_dk : 1.0;
+    const double scM = ITAB ? a.mass_scale * a.inv_dm : a.mass_scale;
 
-        if (a.bd_entity && __ldg(a.bd_entity + g)) {
+    const int64_t nb = a.b1 - a.b0;
+    for (int64_t i = blockIdx.x * (int64_t)S::GROUPS + grp; i < nb; i += (int64_t)gridDim.x * S::GROUPS) {
+        EntHdr h;
+        {
+            const int4 *hp = reinterpret_cast<const int4 *>(a.hdr + i);
+            reinterpret_cast<int4 *>(&h)[0] = __ldg(hp);
+            reinterpret_cast<int4 *>(&h)[1] = __ldg(hp + 1);
+        }
+        const int m = h.m, L = h.L, r = h.rows;
+        double2 *out = a.vals + h.valoff;
+
+        if (a.bd_entity && h.bd) {
             // Dirichlet entity: identity rows (MatZeroRowsColumns puts `diag` on the diagonal)
-            const int sp = __ldg(a.selfpos + g);
-            for (int it = lane; it < r * L; it += G) {
-                int d = it / L, c = it - d * L;
-                out[it] = make_double2(c == sp + d ? a.diag : 0.0, 0.0);
+            const int sp = h.selfpos;
+            for (int it = lane; it < r * L; it += 32) {
+                const int d = it / L, c = it - d * L;
+                __stcs(out + it, make_double2(c == sp + d ? a.diag : 0.0, 0.0));
             }
             continue;
         }
 
-        const int32_t i0 = __ldg(a.inc_ptr + g), m = __ldg(a.inc_ptr + g + 1) - i0;
-        for (int d0 = 0; d0 < r; d0 += a.rc) {
-            const int rcur = min(a.rc, r - d0);
-            for (int it = lane; it < rcur * L; it += G) buf[it] = make_double2(0.0, 0.0);
-            for (int ia = 0; ia < m; ++ia) {
-                group_sync<G>(mask);  // previous pass (or the zeroing) finished; s_rec reusable
-                if (lane < 2)
-                    reinterpret_cast<int4 *>(rec)[lane] = __ldg(reinterpret_cast<const int4 *>(a.rec + i0 + ia) + lane);
-                group_sync<G>(mask);
-                const int64_t t = rec->elem;
-                const int rslot = rec->slot;
-                const unsigned bdm = a.bd_entity ? rec->bdmask : 0u;
-                double gf[12];
-                {
-                    const double2 *gp = reinterpret_cast<const double2 *>(a.geo + t * 12);
+        const int rc = min(r, a.bufstride / L);  // rows per pass (>= 1: bufstride >= max row length)
+        for (int d0 = 0; d0 < r; d0 += rc) {
+            const int rcur = min(rc, r - d0);
+            for (int it = lane; it < rcur * L; it += 32) buf[it] = make_double2(0.0, 0.0);
+            for (int c0 = 0; c0 < m; c0 += S::MC) {
+                const int mc = min((int)S::MC, m - c0);
+                __syncwarp();  // tile zeroed / previous chunk consumed
+                if (lane < 2 * mc)
+                    reinterpret_cast<int4 *>(rec)[lane] =
+                        __ldg(reinterpret_cast<const int4 *>(a.rec + h.inc0 + c0) + lane);
+                __syncwarp();
+                for (int ia = 0; ia < mc; ++ia) {
+                    const IncRecord *rp = rec + ia;
+                    const int64_t t = rp->elem;
+                    const int rslot = rp->slot;
+                    const unsigned bdm = a.bd_entity ? rp->bdmask : 0u;
+                    double gf[12];
+                    {
+                        const double2 *gp = reinterpret_cast<const double2 *>(a.geo + t * 12);
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        double2 v = __ldg(gp + i);
-                        gf[2 * i] = v.x;
-                        gf[2 * i + 1] = v.y;
+                        for (int q = 0; q < 6; ++q) {
+                            const double2 v = __ldg(gp + q);
+                            gf[2 * q] = v.x;
+                            gf[2 * q + 1] = v.y;
+                        }
                     }
-                }
-                const uint32_t cd = __ldg(a.code + t);
-                for (int it = lane; it < rcur * O::n; it += G) {
-                    const int dd = it / O::n, k = it - dd * O::n;
-                    int ks, kd;
-                    slot_of_local<P>(k, ks, kd);
-                    if ((bdm >> ks) & 1u) continue;  // Dirichlet column: stays zero
-                    double s1, s2;
-                    const int Jx = expanded_of_slot<P>(rslot, d0 + dd, cd, s1);
-                    const int Kx = expanded_of_slot<P>(ks, kd, cd, s2);
-                    double kk, mm;
-                    if (a.itable) {
-                        contract12i(a.itable + ((int64_t)Jx * O::nexp + Kx) * 12, gf, kk, mm);
-                        kk *= a.inv_dk;
-                        mm *= a.inv_dm;
-                    } else {
-                        contract12(a.table + ((int64_t)Jx * O::nexp + Kx) * 12, gf, kk, mm);
+                    const uint32_t cd = __ldg(a.code + t);
+                    // the lane's columns in this element: expanded function, sign, tile position
+                    int cxi[S::NC], cpos[S::NC];
+                    bool cneg[S::NC];
+#pragma unroll
+                    for (int j = 0; j < S::NC; ++j) {
+                        cxi[j] = -1, cpos[j] = 0, cneg[j] = false;
+                        if (cks[j] >= 0 && !((bdm >> cks[j]) & 1u)) {  // Dirichlet column: stays zero
+                            double s2;
+                            cxi[j] = expanded_of_slot<P>(cks[j], ckd[j], cd, s2);
+                            cneg[j] = s2 < 0.0;
+                            cpos[j] = rp->slotpos[cks[j]] + ckd[j];
+                        }
                     }
-                    const double s = s1 * s2;
-                    double2 *dst = buf + dd * L + rec->slotpos[ks] + kd;
-                    double2 cur = *dst;
-                    cur.x += s * kk;
-                    cur.y += s * (a.mass_scale * mm);
-                    *dst = cur;
+                    for (int dd = 0; dd < rcur; ++dd) {
+                        double s1;
+                        const int Jx = expanded_of_slot<P>(rslot, d0 + dd, cd, s1);
+                        const int64_t jbase = (int64_t)Jx * O::nexp;
+                        const double sK = s1 * scK, sM = s1 * scM;
+                        double2 *brow = buf + dd * L;
+#pragma unroll
+                        for (int j0 = 0; j0 < S::NC; j0 += S::JB) {
+                            TabEntry<ITAB> e[S::JB];
+#pragma unroll
+                            for (int jj = 0; jj < S::JB; ++jj)
+                                if (j0 + jj < S::NC) e[jj].load(a, jbase + max(cxi[j0 + jj], 0));
+#pragma unroll
+                            for (int jj = 0; jj < S::JB; ++jj) {
+                                const int j = j0 + jj;
+                                if (j < S::NC) {
+                                    double kk, mm;
+                                    e[jj].contract(gf, kk, mm);
+                                    if (cxi[j] >= 0) {
+                                        double2 cur = brow[cpos[j]];
+                                        cur.x = fma(cneg[j] ? -sK : sK, kk, cur.x);
+                                        cur.y = fma(cneg[j] ? -sM : sM, mm, cur.y);
+                                        brow[cpos[j]] = cur;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();  // the next element may touch the same positions from other lanes
                 }
             }
-            group_sync<G>(mask);
             double2 *o2 = out + (int64_t)d0 * L;
-            for (int it = lane; it < rcur * L; it += G) o2[it] = buf[it];
-            group_sync<G>(mask);
+            for (int it = lane; it < rcur * L; it += 32) __stcs(o2 + it, buf[it]);
+            __syncwarp();
         }
     }
 }
@@ -575,33 +655,30 @@ static int launch_assemble_small(const pg_plan *pl, AsmArgs a, cudaStream_t st) 
     return PG_OK;
 }
 
-template <int P, int G, int THREADS>
+template <int P, bool ITAB>
 static int launch_assemble(const pg_plan *pl, AsmArgs a, cudaStream_t st) {
-    constexpr int GROUPS = THREADS / G;
+    using S = Gen<P>;
     const int L = pl->max_rowlen;
-    int rmax = std::max(ndof_edge(pl->p), std::max(ndof_face(pl->p), ndof_volume(pl->p)));
-    // shared tile budget per block: keep >= 2 blocks per SM when possible
-    const size_t budget = 100 * 1024;
-    size_t per_group = (budget - GROUPS * sizeof(IncRecord)) / GROUPS;
-    int rc = (int)std::min<size_t>(rmax, per_group / ((size_t)L * 16));
-    if (rc < 1) {
-        // one row does not fit the default budget: take (almost) the whole SM
-        const size_t big = 220 * 1024;
-        per_group = (big - GROUPS * sizeof(IncRecord)) / GROUPS;
-        rc = (int)std::min<size_t>(rmax, per_group / ((size_t)L * 16));
-        PG_REQUIRE(rc >= 1, PG_ERANGE, "pg_assemble: row length %d does not fit in shared memory", L);
-    }
-    a.rc = rc;
-    a.bufstride = rc * L;
-    const size_t smem = GROUPS * sizeof(IncRecord) + (size_t)GROUPS * a.bufstride * 16;
-    auto kern = assemble_kernel<P, G, THREADS>;
+    const int rmax = std::max(ndof_edge(pl->p), std::max(ndof_face(pl->p), ndof_volume(pl->p)));
+    // tile per warp: at least one row; aim at min(rmax, 3) rows (p <= 4) while >= 8 warps fit per SM
+    const size_t budget = 216 * 1024;
+    const size_t recs = S::MC * sizeof(IncRecord);
+    const size_t want = (size_t)L * 16 * (pl->p <= 4 ? std::min(rmax, 3) : 1) + recs;
+    int warps = (int)std::min<size_t>(32, budget / want);
+    if (warps < 8) warps = (int)std::min<size_t>(8, budget / ((size_t)L * 16 + recs));
+    warps -= warps % S::GROUPS;
+    PG_REQUIRE(warps >= S::GROUPS, PG_ERANGE, "pg_assemble: row length %d does not fit in shared memory", L);
+    a.bufstride = (int)((budget / warps - recs) / 16);
+    a.rc = std::min(rmax, a.bufstride / L);
+    const size_t smem = S::GROUPS * (recs + (size_t)a.bufstride * 16);
+    auto kern = assemble_kernel<P, ITAB>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    PG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    PG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * S::GROUPS, smem));
     PG_REQUIRE(occ >= 1, PG_ERANGE, "pg_assemble: kernel does not fit on an SM (smem %zu)", smem);
     const int64_t nb = pl->b1 - pl->b0;
-    int64_t grid = std::min<int64_t>((nb + GROUPS - 1) / GROUPS, (int64_t)kNumSMs * occ * 4);
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(a);
+    const int64_t grid = std::min<int64_t>((nb + S::GROUPS - 1) / S::GROUPS, (int64_t)kNumSMs * occ);
+    kern<<<(unsigned)grid, 32 * S::GROUPS, smem, st>>>(a);
     PG_LAUNCH_OK();
     return PG_OK;
 }
@@ -629,7 +706,7 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
         // integer codes of the table (lazily built, cached in the plan for this table pointer)
         const int64_t npairs = (int64_t)pg_nexp(pl->p) * pg_nexp(pl->p);
         if (pl->itable_src != table) {
-            if (!pl->itable) PG_CUDA_OK(cudaMalloc((void **)&pl->itable, npairs * 12 * sizeof(uint32_t)));
+            if (!pl->itable) PG_CUDA_OK(cudaMalloc((void **)&pl->itable, npairs * 12 * sizeof(int32_t)));
             build_itable_kernel<<<(unsigned)((npairs * 12 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
                 npairs, pl->p, table, pl->itable);
             PG_LAUNCH_OK();
@@ -646,10 +723,10 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
     switch (pl->p) {
         case 1: return launch_assemble_small<1>(pl, a, st);
         case 2: return launch_assemble_small<2>(pl, a, st);
-        case 3: return launch_assemble<3, 32, 128>(pl, a, st);
-        case 4: return launch_assemble<4, 32, 128>(pl, a, st);
-        case 5: return launch_assemble<5, 32, 128>(pl, a, st);
-        case 6: return launch_assemble<6, 32, 128>(pl, a, st);
+        case 3: return launch_assemble<3, true>(pl, a, st);
+        case 4: return launch_assemble<4, true>(pl, a, st);
+        case 5: return launch_assemble<5, true>(pl, a, st);
+        case 6: return launch_assemble<6, false>(pl, a, st);
     }
     set_error("pg_assemble: bad order %d", pl->p);
     return PG_EINVAL;
