@@ -32,7 +32,7 @@ struct AsmArgs {
     const double *geo;
     const uint32_t *code;
     const double *table;
-    const int32_t *itable;     // p = 3..5: exact integer numerators of the table, null otherwise
+    const int32_t *itable;     // p >= 3: table in gather layout (int32 numerators; fp64 at p = 6)
     double inv_dk, inv_dm;     // 1/DK, 1/DM of the integer codes
     double mass_scale, diag;
     double2 *vals;
@@ -49,13 +49,25 @@ __host__ __device__ inline double int_scale_m(int p) {
     return p == 3 ? 362880.0 : p == 4 ? 39916800.0 : p == 5 ? 6227020800.0 : 0.0;
 }
 
-__global__ void build_itable_kernel(int64_t npairs, int p, const double *__restrict__ table,
+// itable[Jx][q][Kx][4]: quad q = 0..2 of the 12 numerators of the pair (Jx, Kx); the lanes of a
+// warp read consecutive column functions Kx, so each 16-byte quad load touches few 128-byte lines
+__global__ void build_itable_kernel(int64_t nexp, int p, const double *__restrict__ table,
                                     int32_t *__restrict__ itable) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= npairs * 12) return;
+    if (i >= nexp * nexp * 12) return;
     const int c = (int)(i % 12);
+    const int64_t pair = i / 12, jx = pair / nexp, kx = pair - jx * nexp;
     const double v = table[i] * (c < 6 ? int_scale_k(p) : int_scale_m(p));
-    itable[i] = (int32_t)rint(v);
+    itable[(((jx * 3 + (c >> 2)) * nexp) + kx) * 4 + (c & 3)] = (int32_t)rint(v);
+}
+
+// p = 6 (numerators exceed 32 bits): the fp64 table in the same layout, dtable[Jx][q][Kx][2], q = 0..5
+__global__ void build_dtable_kernel(int64_t nexp, const double *__restrict__ table, double *__restrict__ dtable) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nexp * nexp * 12) return;
+    const int c = (int)(i % 12);
+    const int64_t pair = i / 12, jx = pair / nexp, kx = pair - jx * nexp;
+    dtable[(((jx * 6 + (c >> 1)) * nexp) + kx) * 2 + (c & 1)] = table[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -85,9 +97,9 @@ struct TabEntry;
 template <>
 struct TabEntry<true> {  // exact integer numerators
     int4 w[3];
-    __device__ __forceinline__ void load(const AsmArgs &a, int64_t e) {
-        const int4 *q = reinterpret_cast<const int4 *>(a.itable) + e * 3;
-        w[0] = __ldg(q), w[1] = __ldg(q + 1), w[2] = __ldg(q + 2);
+    __device__ __forceinline__ void load(const AsmArgs &a, int64_t jx, int kx, int nexp) {
+        const int4 *q = reinterpret_cast<const int4 *>(a.itable) + jx * 3 * nexp + kx;
+        w[0] = __ldg(q), w[1] = __ldg(q + nexp), w[2] = __ldg(q + 2 * nexp);
     }
     __device__ __forceinline__ void contract(const double (&g)[12], double &k, double &m) const {
         k = g[0] * (double)w[0].x;
@@ -107,10 +119,10 @@ struct TabEntry<true> {  // exact integer numerators
 template <>
 struct TabEntry<false> {  // fp64 table
     double2 w[6];
-    __device__ __forceinline__ void load(const AsmArgs &a, int64_t e) {
-        const double2 *q = reinterpret_cast<const double2 *>(a.table) + e * 6;
+    __device__ __forceinline__ void load(const AsmArgs &a, int64_t jx, int kx, int nexp) {
+        const double2 *q = reinterpret_cast<const double2 *>(a.itable) + jx * 6 * nexp + kx;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i);
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i * nexp);
     }
     __device__ __forceinline__ void contract(const double (&g)[12], double &k, double &m) const {
         k = g[0] * w[0].x;
@@ -128,8 +140,25 @@ struct TabEntry<false> {  // fp64 table
     }
 };
 
+// contraction of one loaded table entry and its add (or first-touch store) into the tile
+template <bool ITAB>
+__device__ __forceinline__ void add_entry(const TabEntry<ITAB> &e, const double (&gf)[12], double2 *dst, double sK,
+                                          double sM, bool live, bool neg, bool first, bool zero) {
+    double kk, mm;
+    e.contract(gf, kk, mm);
+    if (live) {
+        double2 cur = make_double2(0.0, 0.0);
+        if (!first) cur = *dst;
+        cur.x = fma(neg ? -sK : sK, kk, cur.x);
+        cur.y = fma(neg ? -sM : sM, mm, cur.y);
+        *dst = cur;
+    } else if (zero) {  // Dirichlet column touched first: explicit zero
+        *dst = make_double2(0.0, 0.0);
+    }
+}
+
 template <int P, bool ITAB>
-__global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
+__device__ __forceinline__ void assemble_body(const AsmArgs &a) {
     using O = Ord<P>;
     using S = Gen<P>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,10 +204,10 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
         const int rc = min(r, a.bufstride / L);  // rows per pass (>= 1: bufstride >= max row length)
         for (int d0 = 0; d0 < r; d0 += rc) {
             const int rcur = min(rc, r - d0);
-            for (int it = lane; it < rcur * L; it += 32) buf[it] = make_double2(0.0, 0.0);
+            // no zero fill: the element that first touches a column stores (firstmask), later ones add
             for (int c0 = 0; c0 < m; c0 += S::MC) {
                 const int mc = min((int)S::MC, m - c0);
-                __syncwarp();  // tile zeroed / previous chunk consumed
+                __syncwarp();  // previous chunk consumed
                 if (lane < 2 * mc)
                     reinterpret_cast<int4 *>(rec)[lane] =
                         __ldg(reinterpret_cast<const int4 *>(a.rec + h.inc0 + c0) + lane);
@@ -188,6 +217,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
                     const int64_t t = rp->elem;
                     const int rslot = rp->slot;
                     const unsigned bdm = a.bd_entity ? rp->bdmask : 0u;
+                    const unsigned fm = rp->firstmask;
                     double gf[12];
                     {
                         const double2 *gp = reinterpret_cast<const double2 *>(a.geo + t * 12);
@@ -201,43 +231,38 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
                     const uint32_t cd = __ldg(a.code + t);
                     // the lane's columns in this element: expanded function, sign, tile position
                     int cxi[S::NC], cpos[S::NC];
-                    bool cneg[S::NC];
+                    bool cneg[S::NC], cfirst[S::NC], czero[S::NC];
 #pragma unroll
                     for (int j = 0; j < S::NC; ++j) {
-                        cxi[j] = -1, cpos[j] = 0, cneg[j] = false;
-                        if (cks[j] >= 0 && !((bdm >> cks[j]) & 1u)) {  // Dirichlet column: stays zero
-                            double s2;
-                            cxi[j] = expanded_of_slot<P>(cks[j], ckd[j], cd, s2);
-                            cneg[j] = s2 < 0.0;
+                        cxi[j] = -1, cpos[j] = 0, cneg[j] = cfirst[j] = czero[j] = false;
+                        if (cks[j] >= 0) {
+                            const bool bdc = (bdm >> cks[j]) & 1u;  // Dirichlet column: zero
+                            cfirst[j] = (fm >> cks[j]) & 1u;
                             cpos[j] = rp->slotpos[cks[j]] + ckd[j];
+                            czero[j] = bdc && cfirst[j];
+                            if (!bdc) {
+                                double s2;
+                                cxi[j] = expanded_of_slot<P>(cks[j], ckd[j], cd, s2);
+                                cneg[j] = s2 < 0.0;
+                            }
                         }
                     }
                     for (int dd = 0; dd < rcur; ++dd) {
                         double s1;
                         const int Jx = expanded_of_slot<P>(rslot, d0 + dd, cd, s1);
-                        const int64_t jbase = (int64_t)Jx * O::nexp;
                         const double sK = s1 * scK, sM = s1 * scM;
                         double2 *brow = buf + dd * L;
 #pragma unroll
                         for (int j0 = 0; j0 < S::NC; j0 += S::JB) {
-                            TabEntry<ITAB> e[S::JB];
+                            TabEntry<ITAB> e[S::JB];  // all loads of the batch in flight before the first use
 #pragma unroll
                             for (int jj = 0; jj < S::JB; ++jj)
-                                if (j0 + jj < S::NC) e[jj].load(a, jbase + max(cxi[j0 + jj], 0));
+                                if (j0 + jj < S::NC) e[jj].load(a, Jx, max(cxi[j0 + jj], 0), O::nexp);
 #pragma unroll
-                            for (int jj = 0; jj < S::JB; ++jj) {
-                                const int j = j0 + jj;
-                                if (j < S::NC) {
-                                    double kk, mm;
-                                    e[jj].contract(gf, kk, mm);
-                                    if (cxi[j] >= 0) {
-                                        double2 cur = brow[cpos[j]];
-                                        cur.x = fma(cneg[j] ? -sK : sK, kk, cur.x);
-                                        cur.y = fma(cneg[j] ? -sM : sM, mm, cur.y);
-                                        brow[cpos[j]] = cur;
-                                    }
-                                }
-                            }
+                            for (int jj = 0; jj < S::JB; ++jj)
+                                if (j0 + jj < S::NC)
+                                    add_entry(e[jj], gf, brow + cpos[j0 + jj], sK, sM, cxi[j0 + jj] >= 0,
+                                              cneg[j0 + jj], cfirst[j0 + jj], czero[j0 + jj]);
                         }
                     }
                     __syncwarp();  // the next element may touch the same positions from other lanes
@@ -248,6 +273,16 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
             __syncwarp();
         }
     }
+}
+
+// p = 5 would take 162 registers: capped at 128 (4 blocks per SM); the others fit on their own
+template <int P, bool ITAB>
+__global__ void __launch_bounds__(128) assemble_kernel(const AsmArgs a) {
+    assemble_body<P, ITAB>(a);
+}
+template <int P, bool ITAB>
+__global__ void __launch_bounds__(128, 4) assemble_kernel_capped(const AsmArgs a) {
+    assemble_body<P, ITAB>(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -671,7 +706,8 @@ static int launch_assemble(const pg_plan *pl, AsmArgs a, cudaStream_t st) {
     a.bufstride = (int)((budget / warps - recs) / 16);
     a.rc = std::min(rmax, a.bufstride / L);
     const size_t smem = S::GROUPS * (recs + (size_t)a.bufstride * 16);
-    auto kern = assemble_kernel<P, ITAB>;
+    void (*kern)(const AsmArgs);
+    if constexpr (P == 5) kern = assemble_kernel_capped<P, ITAB>; else kern = assemble_kernel<P, ITAB>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * S::GROUPS, smem));
@@ -702,19 +738,28 @@ extern "C" int pg_assemble(const pg_plan *pl, const double *geo, const uint32_t 
     a.bd_entity = apply_dirichlet ? pl->bd_entity : nullptr;
     a.geo = geo, a.code = code, a.table = table;
     a.itable = nullptr, a.inv_dk = a.inv_dm = 0.0;
-    if (pl->p >= 3 && pl->p <= 5) {
-        // integer codes of the table (lazily built, cached in the plan for this table pointer)
-        const int64_t npairs = (int64_t)pg_nexp(pl->p) * pg_nexp(pl->p);
+    if (pl->p >= 3) {
+        // gather-friendly copy of the table (lazily built, cached in the plan for this table pointer):
+        // exact integer numerators for p <= 5, fp64 for p = 6
+        const int64_t nexp = pg_nexp(pl->p), nval = nexp * nexp * 12;
+        const bool ints = pl->p <= 5;
         if (pl->itable_src != table) {
-            if (!pl->itable) PG_CUDA_OK(cudaMalloc((void **)&pl->itable, npairs * 12 * sizeof(int32_t)));
-            build_itable_kernel<<<(unsigned)((npairs * 12 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-                npairs, pl->p, table, pl->itable);
+            if (!pl->itable)
+                PG_CUDA_OK(cudaMalloc((void **)&pl->itable, nval * (ints ? sizeof(int32_t) : sizeof(double))));
+            const unsigned nblk = (unsigned)((nval + 255) / 256);
+            if (ints)
+                build_itable_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(nexp, pl->p, table, pl->itable);
+            else
+                build_dtable_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(nexp, table,
+                                                                            reinterpret_cast<double *>(pl->itable));
             PG_LAUNCH_OK();
             pl->itable_src = table;
         }
         a.itable = pl->itable;
-        a.inv_dk = 1.0 / int_scale_k(pl->p);
-        a.inv_dm = 1.0 / int_scale_m(pl->p);
+        if (ints) {
+            a.inv_dk = 1.0 / int_scale_k(pl->p);
+            a.inv_dm = 1.0 / int_scale_m(pl->p);
+        }
     }
     a.mass_scale = mass_scale, a.diag = diag;
     a.vals = reinterpret_cast<double2 *>(vals);

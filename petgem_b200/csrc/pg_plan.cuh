@@ -63,6 +63,6 @@ struct pg_plan {
     int max_rowlen = 0;
     uint8_t *bd_entity = nullptr;   // [nEnt] own copy, set by pg_plan_set_dirichlet
     // p = 3..5: exact integer codes of the reference tensors (built lazily by pg_assemble from `table`)
-    mutable int32_t *itable = nullptr;       // [nexp*nexp][12] numerators
+    mutable int32_t *itable = nullptr;       // gather-layout table: int32 numerators (p<=5) / fp64 (p=6)
     mutable const double *itable_src = nullptr;
 };
