@@ -371,6 +371,71 @@ def bicgstab(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, 
     return SolveResult(x, maxit, hist, False, "maxit")
 
 
+def tfqmr(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None):
+    """Left-preconditioned transpose-free QMR (KSPTFQMR; Freund 1993, Saad Alg. 7.8): two operator
+    applications per iteration, convergence on the quasi-residual bound tau*sqrt(m+1)."""
+    n, dev = op.n, b.device
+    vk = VecKernels(n, dev, op.ctx, kmax=4)
+    z = lambda: torch.zeros((n,), dtype=_C128, device=dev)  # noqa: E731
+    x, r0, w, u, v, d, Au, tmp = z(), z(), z(), z(), z(), z(), z(), z()
+    sc = torch.zeros((8,), dtype=_C128, device=dev)
+    one = torch.ones((1,), dtype=_C128, device=dev)
+    op.precond(b, r0)
+    tau = math.sqrt(vk.nrm2sq(r0, sc)[0].real.item())
+    if tau == 0.0:
+        return SolveResult(x, 0, [0.0], True, "zero rhs")
+    tol = max(rtol * tau, atol)
+    w.copy_(r0)
+    u.copy_(r0)
+    op.apply(u, v, tmp)
+    Au.copy_(v)
+    theta, eta, rho = 0.0, 0.0 + 0.0j, complex(tau * tau)
+    hist = [tau]
+    m = 0
+    for it in range(1, maxit + 1):
+        sigma = complex(vk.dot(r0, v, sc)[0].item())
+        if sigma == 0.0:
+            return SolveResult(x, it - 1, hist, False, "breakdown sigma")
+        alpha = rho / sigma
+        for half in (0, 1):
+            if half == 1:  # u_{m+1} = u_m - alpha v_m
+                sc[1] = -alpha
+                vk.axpy(sc[1:2], v, u)
+                op.apply(u, Au, tmp)
+            sc[1] = -alpha
+            vk.axpy(sc[1:2], Au, w)                          # w -= alpha B u
+            sc[2] = theta * theta * eta / alpha
+            vk.aypx(sc[2:3], u, d)                           # d = u + (theta^2 eta / alpha) d
+            wn = math.sqrt(vk.nrm2sq(w, sc)[0].real.item())
+            theta = wn / tau
+            c = 1.0 / math.sqrt(1.0 + theta * theta)
+            tau = tau * theta * c
+            eta = c * c * alpha
+            sc[3] = eta
+            vk.axpy(sc[3:4], d, x)
+            m += 1
+            res = tau * math.sqrt(m + 1.0)
+            if res <= tol:
+                hist.append(res)
+                if monitor:
+                    monitor(it, res)
+                return SolveResult(x, it, hist, True, "rtol")
+        hist.append(res)
+        if monitor:
+            monitor(it, res)
+        rho_new = complex(vk.dot(r0, w, sc)[0].item())
+        if rho == 0.0 or rho_new == 0.0:
+            return SolveResult(x, it, hist, False, "breakdown rho")
+        beta = rho_new / rho
+        rho = rho_new
+        sc[1], sc[2] = beta, beta * beta
+        vk.axpbypcz(sc[1:2], Au, sc[2:3], v, None, None, v)  # v = beta (B u_m + beta v)
+        vk.aypx(sc[1:2], w, u)                               # u = w + beta u
+        op.apply(u, Au, tmp)
+        vk.axpy(one, Au, v)                                  # v += B u
+    return SolveResult(x, maxit, hist, False, "maxit")
+
+
 def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None, check_every=10,
          max_seconds=None):
     """Conjugate-orthogonal CG for the complex SYMMETRIC system (KSPCG with -ksp_cg_type symmetric):
@@ -444,7 +509,7 @@ def parse_petsc_options(path_or_text):
 
 
 def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, monitor=None) -> SolveResult:
-    """KSP front end: ksp_type gmres|bcgs, pc_type none|jacobi (sor is mapped to jacobi
+    """KSP front end: ksp_type gmres|bcgs|tfqmr|cg (symmetric), pc_type none|jacobi (sor is mapped to jacobi
     with a warning: PETSc's SOR sweep is sequential), ksp_rtol,
     ksp_gmres_restart, ksp_max_it."""
     o = dict(options or {})
@@ -459,8 +524,10 @@ def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, 
         return gmres(op, b, rtol=rtol, restart=int(o.get("ksp_gmres_restart", 30)), maxit=maxit, monitor=monitor)
     if ksp in ("bcgs", "bicgstab"):
         return bicgstab(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
+    if ksp == "tfqmr":
+        return tfqmr(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
     if ksp == "cg":
         if str(o.get("ksp_cg_type", "symmetric")) != "symmetric":
             raise ValueError("A is complex symmetric, not Hermitian: use -ksp_cg_type symmetric")
         return cocg(op, b, rtol=rtol, maxit=maxit, monitor=monitor)
-    raise ValueError("unsupported ksp_type %r (gmres, bcgs, cg)" % ksp)
+    raise ValueError("unsupported ksp_type %r (gmres, bcgs, tfqmr, cg)" % ksp)

@@ -502,6 +502,10 @@ def test_krylov_on_reference_petsc_fixture(oracle):
                               "ksp_max_it": 4000})
     assert res.converged
     assert np.linalg.norm(res.x.cpu().numpy() - xd) <= 1e-6 * np.linalg.norm(xd)
+    # -ksp_type tfqmr: transpose-free QMR on the same system
+    rest = krylov.solve(A, b, {"ksp_type": "tfqmr", "pc_type": "jacobi", "ksp_rtol": 1e-10, "ksp_max_it": 20000})
+    assert rest.converged, (rest.reason, rest.iterations, rest.residuals[-1])
+    assert np.linalg.norm(rest.x.cpu().numpy() - xd) <= 1e-6 * np.linalg.norm(xd)
 
 
 def test_bad_arguments_fail_loudly(topo):
