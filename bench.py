@@ -215,14 +215,14 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # time-to-solution per CSEM source on BASELINE configs[1] (~1 M tets, p=1, single source, 1 GPU)
 # ---------------------------------------------------------------------------------------------
-def csem_rhs_device(tab, p, plan, dev):
-    """b for a unit x-directed dipole at the centroid of the element nearest to the box centre
-    (solver.py:247-316), in the plan's numbering, owned rows only; Dirichlet rows zeroed."""
+def csem_rhs_device(tab, p, plan, dev, src=(1750.0, 1750.0, -975.0)):
+    """b for a unit x-directed dipole at the centroid of the element nearest to `src` (default: the
+    box centre) (solver.py:247-316), in the plan's numbering, owned rows only; Dirichlet rows zeroed."""
     import torch
 
     from petgem_b200 import hvfem
 
-    src = np.array([1750.0, 1750.0, -975.0])
+    src = np.asarray(src, dtype=np.float64)
     cen = tab["nodes"][tab["elemsN"]].mean(axis=1)
     te = int(np.argmin(((cen - src) ** 2).sum(axis=1)))
     Xe = tab["nodes"][tab["elemsN"][te]]
@@ -280,6 +280,21 @@ def time_to_solution(dev, m=55, p=1, maxit=20000):
         out[name] = {"seconds": dt, "iterations": res.iterations, "converged": bool(res.converged),
                      "true_rel_residual": float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(b)),
                      "time_to_solution_s": t_asm + dt}
+    # four sources of a tow line sharing A, solved in lockstep: one pass over the matrix per iteration
+    B = torch.stack([csem_rhs_device(tab, p, plan, dev, src=(1750.0 + dx, 1750.0, -975.0))
+                     for dx in (-600.0, -200.0, 200.0, 600.0)], dim=1).contiguous()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    X, results = krylov.solve_multi(A, B, {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-8,
+                                           "ksp_max_it": maxit})
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    Rm = B - A.mult_multi(X)
+    out["cocg+jacobi, 4 sources in lockstep"] = {
+        "seconds": dt, "seconds_per_source": dt / 4, "iterations": results[0].iterations,
+        "converged": bool(results[0].converged.all()),
+        "true_rel_residual_max": float((torch.linalg.vector_norm(Rm, dim=0) / torch.linalg.vector_norm(B, dim=0)).max()),
+        "time_to_solution_per_source_s": (t_asm + dt) / 4}
     return out
 
 
@@ -419,7 +434,7 @@ def main():
     if p == 2 and args.m == 94 and world == 1 and os.path.exists(tpath):
         t = json.load(open(tpath))["assemble_small_kernel<2>"]
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    kname = ("assemble_small_kernel<%d>" if p <= 2 else "assemble_kernel<%d,32,128>") % p
+    kname = ("assemble_small_kernel<%d>" if p <= 2 else "assemble_kernel<%d>") % p
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": asm_ms}
@@ -448,6 +463,23 @@ def main():
     spmv = {"ms": spmv_ms, "gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
             "frac_of_peak": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / (peak * world), "nnz": nnz_total, "rows": rows_total,
             "includes_halo_exchange": world > 1}
+    # four right-hand sides per pass over the matrix (sources sharing A): bytes = 20 nnz + 4 * 40 rows
+    if op.mode in ("single", "p2p"):
+        Xm = torch.ones((plan.local_rows, 4), dtype=torch.complex128, device=dev)
+        Ym = torch.empty_like(Xm)
+        for _ in range(3):
+            op.matmat(Xm, Ym)
+        barrier()
+        ev[0].record()
+        for _ in range(args.steps):
+            op.matmat(Xm, Ym)
+        ev[1].record()
+        barrier()
+        mm_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / args.steps
+        mm_bytes = 20.0 * nnz_total + 4 * 40.0 * rows_total
+        spmv["four_rhs"] = {"ms": mm_ms, "ms_per_rhs": mm_ms / 4, "gbs": mm_bytes / (mm_ms * 1e-3) / 1e9,
+                            "frac_of_peak": mm_bytes / (mm_ms * 1e-3) / 1e9 / (peak * world)}
+        del Xm, Ym
 
     # ---- bounded Krylov run: time per GMRES iteration, time-to-solution if it converges -------------
     solve = None
@@ -469,6 +501,20 @@ def main():
         solve["cocg+jacobi"] = {"rtol": 1e-8, "iterations": res.iterations, "converged": bool(res.converged),
                                 "reason": res.reason, "rel_residual": res.residuals[-1] / res.residuals[0],
                                 "seconds": dt, "ms_per_iteration": 1e3 * dt / max(res.iterations, 1)}
+        if op.mode in ("single", "p2p"):
+            # cost of an iteration with four sources in lockstep (bounded run, not a solve)
+            del res
+            B4 = torch.stack([csem_rhs_device(tab, p, plan, dev, src=(1750.0 + dx, 1750.0, -975.0))
+                              for dx in (-600.0, -200.0, 200.0, 600.0)], dim=1).contiguous()
+            barrier()
+            t0 = time.time()
+            resm = krylov.cocg_multi(op, B4, rtol=1e-8, maxit=min(args.solve_maxit, 200))
+            barrier()
+            dt = time.time() - t0
+            solve["cocg+jacobi, 4 sources in lockstep"] = {
+                "iterations": resm.iterations, "ms_per_iteration": 1e3 * dt / max(resm.iterations, 1),
+                "ms_per_iteration_per_source": 1e3 * dt / max(resm.iterations, 1) / 4}
+            del resm, B4
 
     # ---- time-to-solution on configs[1] (1 GPU only) ---------------------------------------------------
     tts = None

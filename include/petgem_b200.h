@@ -225,6 +225,37 @@ int pg_zcopy_scaled(int64_t n, const double *alpha, int inv_real, const double *
 int pg_dznrm2sq(int64_t n, const double *x, double *out, void *work, void *stream);
 int64_t pg_reduce_workspace_bytes(int kmax);
 
+/* ---------------------------------------------------------------------------
+ * Several right-hand sides at once: K sources (or the two MT polarizations) share A, so the K
+ * solves that the reference runs one after the other (solver.py:584-590, one KSP.solve per
+ * right-hand side) advance in lockstep and the matrix is streamed once per iteration for all of
+ * them.  Vectors are INTERLEAVED: X[(i*k + r)] (complex) = entry i of right-hand side r,
+ * k = 1, 2, 4 or 8 (pad with zero right-hand sides).  Per-right-hand-side scalars are arrays of
+ * k complex numbers in device memory.  work = pg_reduce_workspace_bytes(2*k).
+ * --------------------------------------------------------------------------- */
+/* Y = dscale .* (A X) for k right-hand sides (dscale may be NULL); X is the FULL interleaved block */
+int pg_spmm(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, const double *vals, int k,
+            const double *X, const double *dscale, double *Y, void *stream);
+/* the same through the plan's 2x2 entity blocks (p = 2, k = 2, 4, 8): see pg_spmv_blocked */
+int pg_spmm_blocked(const pg_plan *plan, const int32_t *colstart, const double *vals, int k, const double *X,
+                    const double *dscale, double *Y, void *stream);
+/* Y[:,r] += alpha[r] X[:,r] */
+int pg_zbaxpy(int64_t n, int k, const double *alpha, const double *X, double *Y, void *stream);
+/* Y[:,r] = X[:,r] + beta[r] Y[:,r] */
+int pg_zbaypx(int64_t n, int k, const double *beta, const double *X, double *Y, void *stream);
+/* Y[i,r] = d[i] X[i,r] (PCJACOBI apply for every right-hand side) */
+int pg_zbscale_rows(int64_t n, int k, const double *d, const double *X, double *Y, void *stream);
+/* out[r] = sum_i X[i,r] Y[i,r] (no conjugation) */
+int pg_zbdotu(int64_t n, int k, const double *X, const double *Y, double *out, void *work, void *stream);
+/* out[r] = sum_i |X[i,r]|^2 */
+int pg_zbnrm2sq(int64_t n, int k, const double *X, double *out, void *work, void *stream);
+/* out[r] = a[r] / b[r] (0 where b[r] == 0), out[k + r] = -out[r] */
+int pg_zbdiv(int k, const double *a, const double *b, double *out, void *stream);
+/* fused COCG update: X += alpha P, R -= alpha Q (alpha2 = {alpha[k], -alpha[k]} from pg_zbdiv),
+ * Z = dinv .* R (dinv NULL: Z = R), out[r] = R[:,r]^T Z[:,r], out[k + r] = |Z[:,r]|^2 */
+int pg_cocg_step(int64_t n, int k, const double *alpha2, const double *P, const double *Q, const double *dinv,
+                 double *X, double *R, double *Z, double *out, void *work, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -101,6 +101,15 @@ SIGNATURES = {
     "pg_zcopy_scaled": (C.c_int, [_i64, _p, _i32, _p, _p, _p]),
     "pg_dznrm2sq": (C.c_int, [_i64, _p, _p, _p, _p]),
     "pg_reduce_workspace_bytes": (_i64, [_i32]),
+    "pg_spmm": (C.c_int, [_i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "pg_spmm_blocked": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p]),
+    "pg_zbaxpy": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
+    "pg_zbaypx": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
+    "pg_zbscale_rows": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
+    "pg_zbdotu": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p]),
+    "pg_zbnrm2sq": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
+    "pg_zbdiv": (C.c_int, [_i32, _p, _p, _p, _p]),
+    "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _LIB = None

@@ -88,6 +88,153 @@ __global__ void __launch_bounds__(256, 6) spmv_blocked2_kernel(int64_t nb, const
     }
 }
 
+// The same for K interleaved right-hand sides (X[i*K + r], see pg_multi.cu): K lanes share a 2x2 block,
+// lane r of them gathers X[c0, r] and X[c0+1, r] -- together the 32*K contiguous bytes of the column
+// entity, which serve 4 nonzeros x K right-hand sides (8 B gathered per nonzero and right-hand side instead
+// of 16) -- and the 8/K lane sets of a group take alternate column entities.
+template <int K>
+__global__ void __launch_bounds__(256) spmm_blocked2_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
+                                                            const int32_t *__restrict__ colstart,
+                                                            const double2 *__restrict__ vals,
+                                                            const double2 *__restrict__ X,
+                                                            const double2 *__restrict__ dscale,
+                                                            double2 *__restrict__ Y) {
+    constexpr int NS = kBG / K;  // column entities per step of a group
+    const int lane = threadIdx.x % kBG;
+    const int r = lane % K, sub = lane / K;
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kBG;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / kBG;
+    const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
+    const uint64_t stream = l2_policy_evict_first();
+    const double2 *Xr = X + r;
+    for (int64_t i = grp; i < nb; i += ngrp) {
+        const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
+        const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
+        const int L = (h1.x >> 16) & 0xffff;
+        const int row = h1.z, cbase = h1.w;
+        const int nc = L >> 1;
+        const double2 *v0 = vals + valoff, *v1 = v0 + L;
+        const int32_t *cs = colstart + cbase;
+        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        int j = sub;
+        for (; j + NS < nc; j += 2 * NS) {  // two column entities per lane in flight
+            const int32_t c0 = ld_stream<1>(cs + j, stream), c1 = ld_stream<1>(cs + j + NS, stream);
+            const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
+            const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+            const double2 q00 = ld_stream<1>(v0 + 2 * (j + NS), stream), q01 = ld_stream<1>(v0 + 2 * (j + NS) + 1, stream);
+            const double2 q10 = ld_stream<1>(v1 + 2 * (j + NS), stream), q11 = ld_stream<1>(v1 + 2 * (j + NS) + 1, stream);
+            const double2 x0 = __ldg(Xr + (int64_t)c0 * K), x1 = __ldg(Xr + ((int64_t)c0 + 1) * K);
+            const double2 z0 = __ldg(Xr + (int64_t)c1 * K), z1 = __ldg(Xr + ((int64_t)c1 + 1) * K);
+            cfma2(a0, p00, x0);
+            cfma2(a1, p10, x0);
+            cfma2(a0, p01, x1);
+            cfma2(a1, p11, x1);
+            cfma2(a0, q00, z0);
+            cfma2(a1, q10, z0);
+            cfma2(a0, q01, z1);
+            cfma2(a1, q11, z1);
+        }
+        if (j < nc) {
+            const int32_t c0 = ld_stream<1>(cs + j, stream);
+            const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
+            const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+            const double2 x0 = __ldg(Xr + (int64_t)c0 * K), x1 = __ldg(Xr + ((int64_t)c0 + 1) * K);
+            cfma2(a0, p00, x0);
+            cfma2(a1, p10, x0);
+            cfma2(a0, p01, x1);
+            cfma2(a1, p11, x1);
+        }
+#pragma unroll
+        for (int o = K; o < kBG; o <<= 1) {  // sum over the lane sets that share right-hand side r
+            a0.x += __shfl_xor_sync(gm, a0.x, o, kBG);
+            a0.y += __shfl_xor_sync(gm, a0.y, o, kBG);
+            a1.x += __shfl_xor_sync(gm, a1.x, o, kBG);
+            a1.y += __shfl_xor_sync(gm, a1.y, o, kBG);
+        }
+        if (sub == 0) {
+            if (dscale) {
+                const double2 d0 = __ldg(dscale + row), d1 = __ldg(dscale + row + 1);
+                a0 = make_double2(d0.x * a0.x - d0.y * a0.y, d0.x * a0.y + d0.y * a0.x);
+                a1 = make_double2(d1.x * a1.x - d1.y * a1.y, d1.x * a1.y + d1.y * a1.x);
+            }
+            Y[(int64_t)row * K + r] = a0;
+            Y[((int64_t)row + 1) * K + r] = a1;
+        }
+    }
+}
+
+// Variant with one lane per column entity and all K right-hand sides in that lane (2K accumulators):
+// no value is loaded twice.  Measured at C3: better at K = 2 (7.3 vs 7.6 ms), worse at K = 4 (12.8 vs
+// 10.6 ms, registers), so it serves K = 2 only.
+template <int K>
+__global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
+                                                                 const int32_t *__restrict__ colstart,
+                                                                 const double2 *__restrict__ vals,
+                                                                 const double2 *__restrict__ X,
+                                                                 const double2 *__restrict__ dscale,
+                                                                 double2 *__restrict__ Y) {
+    const int lane = threadIdx.x % kBG;
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kBG;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / kBG;
+    const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
+    const uint64_t stream = l2_policy_evict_first();
+    for (int64_t i = grp; i < nb; i += ngrp) {
+        const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
+        const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
+        const int L = (h1.x >> 16) & 0xffff;
+        const int row = h1.z, cbase = h1.w;
+        const int nc = L >> 1;
+        const double2 *v0 = vals + valoff, *v1 = v0 + L;
+        const int32_t *cs = colstart + cbase;
+        double2 a0[K], a1[K];
+#pragma unroll
+        for (int r = 0; r < K; ++r) a0[r] = a1[r] = make_double2(0.0, 0.0);
+        for (int j = lane; j < nc; j += kBG) {
+            const int32_t c0 = ld_stream<1>(cs + j, stream);
+            const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
+            const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+            const double2 *xp = X + (int64_t)c0 * K;
+            double2 x0[K], x1[K];
+#pragma unroll
+            for (int r = 0; r < K; ++r) x0[r] = __ldg(xp + r), x1[r] = __ldg(xp + K + r);
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                cfma2(a0[r], p00, x0[r]);
+                cfma2(a1[r], p10, x0[r]);
+                cfma2(a0[r], p01, x1[r]);
+                cfma2(a1[r], p11, x1[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+#pragma unroll
+            for (int o = kBG / 2; o > 0; o >>= 1) {
+                a0[r].x += __shfl_xor_sync(gm, a0[r].x, o, kBG);
+                a0[r].y += __shfl_xor_sync(gm, a0[r].y, o, kBG);
+                a1[r].x += __shfl_xor_sync(gm, a1[r].x, o, kBG);
+                a1[r].y += __shfl_xor_sync(gm, a1[r].y, o, kBG);
+            }
+        }
+        // lanes 0..K-1 store row 0, lanes K..2K-1 row 1 (2K <= 8)
+        double2 mine = a0[0];
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            if (lane == r) mine = a0[r];
+            if (lane == K + r) mine = a1[r];
+        }
+        if (lane < 2 * K) {
+            const int rr = lane / K;
+            if (dscale) {
+                const double2 d = __ldg(dscale + row + rr);
+                mine = make_double2(d.x * mine.x - d.y * mine.y, d.x * mine.y + d.y * mine.x);
+            }
+            Y[(int64_t)row * K + lane] = mine;  // rows row, row+1 are contiguous: [row][K] then [row+1][K]
+        }
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -108,6 +255,28 @@ extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const
         case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
         case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
         default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2);
+    }
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const double *vals, int k, const double *X,
+                               const double *dscale, double *Y, void *stream) {
+    PG_REQUIRE(pl && vals && X && Y, PG_EINVAL, "pg_spmm_blocked: null pointer");
+    PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmm_blocked: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
+    PG_REQUIRE(k == 2 || k == 4 || k == 8, PG_EINVAL, "pg_spmm_blocked: k = %d (2, 4 or 8)", k);
+    const int64_t nb = pl->b1 - pl->b0;
+    if (nb == 0) return PG_OK;
+    const int64_t blocks = std::min<int64_t>((nb * kBG + 255) / 256, (int64_t)kNumSMs * 96);
+    const int32_t *cs = colstart ? colstart : pl->colstart;
+    const double2 *v2 = reinterpret_cast<const double2 *>(vals), *x2 = reinterpret_cast<const double2 *>(X);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
+    double2 *y2 = reinterpret_cast<double2 *>(Y);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (k) {
+        case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
+        case 4: spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
+        default: spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2);
     }
     PG_LAUNCH_OK();
     return PG_OK;

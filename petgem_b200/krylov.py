@@ -98,6 +98,17 @@ class DistContext:
         return xbuf
 
 
+def _exchange_multi(ctx, X, send_idx, send_splits, recv_splits, sendbuf, xbuf):
+    """DistContext.exchange for an interleaved [n, k] block: xbuf = [X | halo rows]."""
+    n, k = X.shape
+    xbuf[:n].copy_(X)
+    torch.index_select(X, 0, send_idx, out=sendbuf)
+    ctx.dist.all_to_all_single(torch.view_as_real(xbuf[n:]).view(-1), torch.view_as_real(sendbuf).view(-1),
+                               output_split_sizes=[2 * k * s for s in recv_splits],
+                               input_split_sizes=[2 * k * s for s in send_splits], group=ctx.group)
+    return xbuf
+
+
 class Operator:
     """y = M^-1 A x on the owned rows, with the halo handled for the caller."""
 
@@ -127,8 +138,9 @@ class Operator:
                     self.halo_entries = next_
                     self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
                     self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
-                    cs = ctx.remap_halo(A.plan.column_starts()) if A.plan is not None else None
-                    self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=A.plan,
+                    pref = getattr(A, "plan_ref", None)
+                    cs = ctx.remap_halo(pref.column_starts()) if pref is not None else None
+                    self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=pref,
                                             colstart=cs, blocked=A.plan is not None)
             if self.mode == "allgather":
                 self.colidx_local = ctx.remap_columns(A.colidx)
@@ -150,6 +162,23 @@ class Operator:
             self.A.mult(x, y, row_scale)
         self.spmv_calls += 1
         return y
+
+    def matmat(self, X: torch.Tensor, Y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
+        """Y = A X for k interleaved right-hand sides (X, Y: [n, k]); one pass over the matrix."""
+        k = int(X.shape[1])
+        if self.mode == "p2p":
+            if getattr(self, "_mm", None) is None or self._mm[0] != k:
+                dev = X.device
+                self._mm = (k, torch.zeros((int(sum(self.send_splits)), k), dtype=_C128, device=dev),
+                            torch.zeros((self.n + self.halo_entries, k), dtype=_C128, device=dev))
+            _exchange_multi(self.ctx, X, self.send_idx, self.send_splits, self.recv_splits, self._mm[1], self._mm[2])
+            self.A_halo.mult_multi(self._mm[2], Y, row_scale)
+        elif self.mode == "allgather":
+            raise NotImplementedError("multi-right-hand-side SpMV needs the neighbour halo (halo='p2p')")
+        else:
+            self.A.mult_multi(X, Y, row_scale)
+        self.spmv_calls += 1
+        return Y
 
     def precond(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         if self.inv_diag is None:
@@ -490,6 +519,121 @@ def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, moni
         if max_seconds is not None and _time.time() - t_start > max_seconds:
             return SolveResult(x, it, hist, False, "time limit")
     return SolveResult(x, maxit, hist, False, "maxit")
+
+
+class MultiSolveResult:
+    """Result of a lockstep solve of k right-hand sides: x is [n, k]."""
+
+    def __init__(self, x, iterations, residuals, converged, reason):
+        self.x, self.iterations, self.residuals = x, iterations, residuals
+        self.converged, self.reason = converged, reason
+
+
+def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, monitor=None, check_every=10,
+               max_seconds=None):
+    """COCG (see cocg) on k right-hand sides in lockstep: B is [n, k], k in {1, 2, 4, 8}.  Per iteration
+    one pass over the matrix for all k (pg_spmm), one fused update/Jacobi/reduction pass (pg_cocg_step),
+    one dot and one AYPX; every right-hand side keeps its own alpha, beta and residual.  Iterates until
+    every right-hand side meets its own tolerance (all-zero right-hand sides are born converged)."""
+    import time as _time
+
+    n, k = int(B.shape[0]), int(B.shape[1])
+    if k not in (1, 2, 4, 8):
+        raise ValueError("cocg_multi: k must be 1, 2, 4 or 8 (pad with zero right-hand sides)")
+    dev = B.device
+    L = lib()
+    ctx = op.ctx if (op.ctx is not None and op.ctx.world > 1) else None
+    work = torch.empty((L.pg_reduce_workspace_bytes(2 * k) // 16,), dtype=_C128, device=dev)
+    Z_ = lambda: torch.zeros((n, k), dtype=_C128, device=dev)  # noqa: E731
+    X, R, Z, P, Q = Z_(), B.contiguous().clone(), Z_(), Z_(), Z_()
+    rho = [torch.zeros((k,), dtype=_C128, device=dev) for _ in range(2)]
+    pq = torch.zeros((k,), dtype=_C128, device=dev)
+    alpha2 = torch.zeros((2 * k,), dtype=_C128, device=dev)
+    beta2 = torch.zeros((2 * k,), dtype=_C128, device=dev)
+    out2 = torch.zeros((2 * k,), dtype=_C128, device=dev)
+    st = stream_ptr
+
+    def reduce_(t):
+        if ctx is not None:
+            ctx.allreduce(t)
+
+    if op.inv_diag is not None:
+        check(L.pg_zbscale_rows(n, k, ptr(op.inv_diag), ptr(R), ptr(Z), st()), "pg_zbscale_rows")
+    else:
+        Z.copy_(R)
+    check(L.pg_zbnrm2sq(n, k, ptr(Z), ptr(out2), ptr(work), st()), "pg_zbnrm2sq")
+    reduce_(out2[:k])
+    bnorm = out2[:k].real.sqrt().cpu().numpy()
+    tol = np.maximum(rtol * bnorm, atol)
+    P.copy_(Z)
+    check(L.pg_zbdotu(n, k, ptr(R), ptr(Z), ptr(rho[0]), ptr(work), st()), "pg_zbdotu")
+    reduce_(rho[0])
+    hist = [bnorm.copy()]
+    if not (bnorm > 0).any():
+        return MultiSolveResult(X, 0, hist, np.ones(k, dtype=bool), "zero rhs")
+    it, cur = 0, 0
+    t_start = _time.time()
+    while it < maxit:
+        for _ in range(min(check_every, maxit - it)):
+            op.matmat(P, Q)
+            check(L.pg_zbdotu(n, k, ptr(P), ptr(Q), ptr(pq), ptr(work), st()), "pg_zbdotu")
+            reduce_(pq)
+            check(L.pg_zbdiv(k, ptr(rho[cur]), ptr(pq), ptr(alpha2), st()), "pg_zbdiv")
+            check(L.pg_cocg_step(n, k, ptr(alpha2), ptr(P), ptr(Q), ptr(op.inv_diag), ptr(X), ptr(R), ptr(Z),
+                                 ptr(out2), ptr(work), st()), "pg_cocg_step")
+            reduce_(out2)
+            rho[cur ^ 1].copy_(out2[:k])
+            check(L.pg_zbdiv(k, ptr(rho[cur ^ 1]), ptr(rho[cur]), ptr(beta2), st()), "pg_zbdiv")
+            check(L.pg_zbaypx(n, k, ptr(beta2), ptr(Z), ptr(P), st()), "pg_zbaypx")
+            cur ^= 1
+            it += 1
+        res2 = out2[k:].real.cpu().numpy()  # the host sync of this batch
+        if not np.isfinite(res2).all():
+            return MultiSolveResult(X, it, hist, np.zeros(k, dtype=bool), "breakdown")
+        res = np.sqrt(res2)
+        hist.append(res)
+        if monitor:
+            monitor(it, res)
+        done = res <= tol
+        if done.all():
+            return MultiSolveResult(X, it, hist, done, "rtol")
+        if max_seconds is not None and _time.time() - t_start > max_seconds:
+            return MultiSolveResult(X, it, hist, done, "time limit")
+    return MultiSolveResult(X, maxit, hist, hist[-1] <= tol, "maxit")
+
+
+def solve_multi(A: CSRMatrix, B: torch.Tensor, options=None, ctx: DistContext = None, monitor=None):
+    """KSP front end for several right-hand sides sharing A: B is [n, nrhs] (any nrhs).  With
+    -ksp_type cg -ksp_cg_type symmetric the right-hand sides advance in lockstep, up to 8 per pass over
+    the matrix (cocg_multi); other solver types run one right-hand side after the other like the
+    reference.  Returns (X [n, nrhs], list of per-batch results)."""
+    o = dict(options or {})
+    ksp = str(o.get("ksp_type", "gmres"))
+    nrhs = int(B.shape[1])
+    X = torch.empty((B.shape[0], nrhs), dtype=_C128, device=B.device)
+    results = []
+    if ksp != "cg":
+        for r in range(nrhs):
+            res = solve(A, B[:, r].contiguous(), o, ctx=ctx, monitor=monitor)
+            X[:, r] = res.x
+            results.append(res)
+        return X, results
+    if str(o.get("ksp_cg_type", "symmetric")) != "symmetric":
+        raise ValueError("A is complex symmetric, not Hermitian: use -ksp_cg_type symmetric")
+    pc = str(o.get("pc_type", "jacobi"))
+    if pc in ("sor", "bjacobi", "asm", "gamg", "lu", "ilu"):
+        pc = "jacobi"
+    op = Operator(A, pc=pc, ctx=ctx, halo="p2p" if ctx is not None and ctx.world > 1 else "auto")
+    rtol, maxit = float(o.get("ksp_rtol", 1e-5)), int(o.get("ksp_max_it", 10000))
+    for r0 in range(0, nrhs, 8):
+        kk = min(8, nrhs - r0)
+        kpad = 1 if kk == 1 else 2 if kk == 2 else 4 if kk <= 4 else 8
+        Bp = torch.zeros((B.shape[0], kpad), dtype=_C128, device=B.device)
+        Bp[:, :kk] = B[:, r0:r0 + kk]
+        res = cocg_multi(op, Bp, rtol=rtol, maxit=maxit, monitor=monitor)
+        X[:, r0:r0 + kk] = res.x[:, :kk]
+        results.append(res)
+    return X, results
 
 
 def parse_petsc_options(path_or_text):

@@ -589,6 +589,20 @@ def test_entity_blocked_spmv_equals_csr(topo, order):
     rp2, ci2 = part.csr()
     yb = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part, blocked=True).mult(x)
     assert torch.linalg.vector_norm(yb - Acsr.mult(x)[cut:]) <= 1e-14 * torch.linalg.vector_norm(yb)
+    # several right-hand sides: blocked SpMM (k lanes per block / lane per block) == CSR SpMM == k SpMVs
+    Apart = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part)
+    Aref_ = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan)
+    assert Aref_.plan is None and Aref_.plan_ref is plan
+    for k in (2, 4, 8):
+        X = torch.randn((plan.N, k), dtype=torch.complex128, generator=gen).to(vals.device)
+        Yc, Yb = Acsr.mult_multi(X), Aref_.mult_multi(X)
+        cols = torch.stack([Acsr.mult(X[:, r].contiguous()) for r in range(k)], dim=1)
+        assert torch.linalg.vector_norm(Yc - cols) <= 1e-14 * torch.linalg.vector_norm(cols)
+        assert torch.linalg.vector_norm(Yb - cols) <= 1e-14 * torch.linalg.vector_norm(cols)
+        Ys = Aref_.mult_multi(X, row_scale=d)
+        assert torch.linalg.vector_norm(Ys - d[:, None] * cols) <= 1e-14 * torch.linalg.vector_norm(Ys)
+        Yp = Apart.mult_multi(X)
+        assert torch.linalg.vector_norm(Yp - cols[cut:]) <= 1e-14 * torch.linalg.vector_norm(Yp)
 
 
 def test_empty_inputs_are_accepted():
@@ -604,3 +618,109 @@ def test_empty_inputs_are_accepted():
     assert L.pg_zmdotc(5, 0, None, 5, None, None, None, None) == 0
     assert L.pg_connectivity_dofs(0, 3, None, None, 0, 0, None, None) == 0
     assert L.pg_zero_rows_columns(0, 0, None, None, None, 1.0, None, None) == 0
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+def test_multi_rhs_kernels_match_numpy(k):
+    """pg_spmm and the per-right-hand-side vector kernels on interleaved [n, k] blocks."""
+    import scipy.sparse as sp
+
+    from petgem_b200._lib import check, lib, ptr, stream_ptr
+    from petgem_b200.device import CSRMatrix
+
+    g = golden("petsc_fixture_system.npz")
+    dev = torch.device("cuda")
+    n = 4184
+    A = CSRMatrix(torch.as_tensor(g["rowptr"], device=dev), torch.as_tensor(g["colidx"], device=dev),
+                  torch.as_tensor(g["vals"], device=dev), n)
+    As = sp.csr_matrix((g["vals"], g["colidx"], g["rowptr"]), shape=(n, n))
+    rng = np.random.default_rng(5 + k)
+    cplx = lambda *s: rng.normal(size=s) + 1j * rng.normal(size=s)  # noqa: E731
+    X, Y0, d = cplx(n, k), cplx(n, k), cplx(n)
+    Xd, dd = torch.as_tensor(X, device=dev), torch.as_tensor(d, device=dev)
+    Y = A.mult_multi(Xd).cpu().numpy()
+    ref = As @ X
+    assert np.abs(Y - ref).max() <= 1e-13 * np.abs(ref).max()
+    # each column equals the single-vector kernel bit for bit up to summation order: compare loosely, and
+    # the Jacobi-scaled epilogue exactly against scaling afterwards
+    Ys = A.mult_multi(Xd, row_scale=dd).cpu().numpy()
+    assert np.abs(Ys - d[:, None] * ref).max() <= 1e-13 * np.abs(d[:, None] * ref).max()
+    L = lib()
+    work = torch.empty((L.pg_reduce_workspace_bytes(2 * k) // 16,), dtype=torch.complex128, device=dev)
+    out = torch.zeros((2 * k,), dtype=torch.complex128, device=dev)
+    Yd = torch.as_tensor(Y0, device=dev)
+    check(L.pg_zbdotu(n, k, ptr(Xd), ptr(Yd), ptr(out), ptr(work), stream_ptr()))
+    ref = (X * Y0).sum(axis=0)
+    assert np.abs(out[:k].cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    check(L.pg_zbnrm2sq(n, k, ptr(Xd), ptr(out), ptr(work), stream_ptr()))
+    ref = (np.abs(X) ** 2).sum(axis=0)
+    assert np.abs(out[:k].cpu().numpy() - ref).max() <= 1e-13 * ref.max()
+    al = cplx(k)
+    ald = torch.as_tensor(al, device=dev)
+    Yd = torch.as_tensor(Y0, device=dev)
+    check(L.pg_zbaxpy(n, k, ptr(ald), ptr(Xd), ptr(Yd), stream_ptr()))
+    assert np.abs(Yd.cpu().numpy() - (Y0 + al * X)).max() <= 1e-14 * np.abs(Y0 + al * X).max()
+    Yd = torch.as_tensor(Y0, device=dev)
+    check(L.pg_zbaypx(n, k, ptr(ald), ptr(Xd), ptr(Yd), stream_ptr()))
+    assert np.abs(Yd.cpu().numpy() - (X + al * Y0)).max() <= 1e-14 * np.abs(X + al * Y0).max()
+    Zd = torch.empty_like(Xd)
+    check(L.pg_zbscale_rows(n, k, ptr(dd), ptr(Xd), ptr(Zd), stream_ptr()))
+    assert np.abs(Zd.cpu().numpy() - d[:, None] * X).max() <= 1e-15 * np.abs(X).max() * np.abs(d).max()
+    # a / b with the zero-denominator rule, and the fused COCG step
+    a, b = cplx(k), cplx(k)
+    b[0] = 0.0
+    q2 = torch.zeros((2 * k,), dtype=torch.complex128, device=dev)
+    a_d, b_d = torch.as_tensor(a, device=dev), torch.as_tensor(b, device=dev)
+    check(L.pg_zbdiv(k, ptr(a_d), ptr(b_d), ptr(q2), stream_ptr()))
+    q = np.where(b == 0, 0.0, a / np.where(b == 0, 1.0, b))
+    assert np.abs(q2[:k].cpu().numpy() - q).max() <= 1e-15 * max(np.abs(q).max(), 1.0)
+    assert np.array_equal(q2[k:].cpu().numpy(), -q2[:k].cpu().numpy())
+    P, Q, X0, R0 = cplx(n, k), cplx(n, k), cplx(n, k), cplx(n, k)
+    a2 = torch.as_tensor(np.concatenate([al, -al]), device=dev)
+    Xs, Rs, Zs = torch.as_tensor(X0, device=dev), torch.as_tensor(R0, device=dev), torch.empty_like(Xd)
+    P_d, Q_d = torch.as_tensor(P, device=dev), torch.as_tensor(Q, device=dev)
+    check(L.pg_cocg_step(n, k, ptr(a2), ptr(P_d), ptr(Q_d), ptr(dd), ptr(Xs), ptr(Rs), ptr(Zs), ptr(out), ptr(work),
+                         stream_ptr()))
+    Xr, Rr = X0 + al * P, R0 - al * Q
+    Zr = d[:, None] * Rr
+    assert np.abs(Xs.cpu().numpy() - Xr).max() <= 1e-14 * np.abs(Xr).max()
+    assert np.abs(Rs.cpu().numpy() - Rr).max() <= 1e-14 * np.abs(Rr).max()
+    assert np.abs(Zs.cpu().numpy() - Zr).max() <= 1e-14 * np.abs(Zr).max()
+    o = out.cpu().numpy()
+    assert np.abs(o[:k] - (Rr * Zr).sum(axis=0)).max() <= 1e-12 * np.abs((Rr * Zr).sum(axis=0)).max()
+    assert np.abs(o[k:] - (np.abs(Zr) ** 2).sum(axis=0)).max() <= 1e-12 * (np.abs(Zr) ** 2).sum(axis=0).max()
+    # bad k fails loudly
+    assert L.pg_spmm(n, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), 3, ptr(Xd), None, ptr(Zd), stream_ptr()) != 0
+
+
+def test_lockstep_multi_source_solve_matches_single(topo, oracle):
+    """Three sources sharing A, solved in lockstep (padded to k = 4): every column agrees with its own
+    single-right-hand-side COCG solve and with the direct solve (receiver tolerance 1e-6)."""
+    import scipy.sparse.linalg as spla
+
+    from petgem_b200 import krylov
+
+    A, b, dofs, omega, mu = _csem_system(topo, oracle, 1)
+    rng = np.random.default_rng(3)
+    n = b.size
+    B = np.stack([b, np.roll(b, 17) * (0.5 - 0.25j), np.zeros(n)], axis=1)  # a shifted source and a dead one
+    B[topo["boundary_dofs_p1"], :] = 0.0
+    Bd = torch.as_tensor(B, device=A.vals.device)
+    opts = {"ksp_type": "cg", "ksp_cg_type": "symmetric", "pc_type": "jacobi", "ksp_rtol": 1e-12,
+            "ksp_max_it": 20000}
+    X, results = krylov.solve_multi(A, Bd, opts)
+    assert len(results) == 1 and results[0].converged.all(), (results[0].reason, results[0].residuals[-1])
+    Xh = X.cpu().numpy()
+    lu = spla.splu(A.to_scipy().tocsc())
+    for r in range(2):
+        xd = lu.solve(B[:, r])
+        assert np.linalg.norm(Xh[:, r] - xd) <= 1e-6 * np.linalg.norm(xd)
+        single = krylov.solve(A, Bd[:, r].contiguous(), opts)
+        assert single.converged
+        assert np.linalg.norm(Xh[:, r] - single.x.cpu().numpy()) <= 1e-8 * np.linalg.norm(xd)
+    assert not Xh[:, 2].any()  # the zero right-hand side stays exactly zero
+    # other solver types fall back to one solve per right-hand side, same answers
+    Xg, resg = krylov.solve_multi(A, Bd[:, :2].contiguous(), {"ksp_type": "gmres", "pc_type": "jacobi",
+                                                               "ksp_rtol": 1e-12, "ksp_max_it": 20000})
+    assert len(resg) == 2 and all(r.converged for r in resg)
+    assert np.linalg.norm(Xg.cpu().numpy() - Xh[:, :2]) <= 1e-6 * np.linalg.norm(Xh[:, :2])

@@ -57,3 +57,33 @@ for name, A in (("csr", CSRMatrix(rowptr, colidx, vals, plan.N)),
 print("hints=%s morton=%d m=%d nnz=%d assemble %.3f ms:" % (os.environ.get("PG_SPMV_HINTS", "1"), args.morton, args.m,
                                                             plan.nnz, asm_ms),
       " ".join("%s %.3f ms %.0f GB/s" % (k, v[0], v[1]) for k, v in out.items()))
+
+# several right-hand sides per pass over the matrix: CSR (pg_spmm) and entity-blocked (pg_spmm_blocked)
+from petgem_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
+
+L = lib()
+for k in (2, 4, 8):
+    X = torch.randn((plan.N, k), dtype=torch.complex128, device=dev)
+    Y1, Y2 = torch.empty_like(X), torch.empty_like(X)
+    res = {}
+    for name in ("csr", "blocked"):
+        def run(Y):
+            if name == "csr":
+                check(L.pg_spmm(plan.N, ptr(rowptr), ptr(colidx), ptr(vals), k, ptr(X), None, ptr(Y), stream_ptr()))
+            else:
+                check(L.pg_spmm_blocked(plan._h, None, ptr(vals), k, ptr(X), None, ptr(Y), stream_ptr()))
+        Y = Y1 if name == "csr" else Y2
+        for _ in range(3):
+            run(Y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            run(Y)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / args.reps
+    err = float((Y1 - Y2).abs().max() / Y1.abs().max())
+    print("k=%d: csr %.3f ms (%.3f/rhs)  blocked %.3f ms (%.3f/rhs)  max rel diff %.1e"
+          % (k, res["csr"], res["csr"] / k, res["blocked"], res["blocked"] / k, err))
+    del X, Y1, Y2
