@@ -256,6 +256,14 @@ int pg_zbdiv(int k, const double *a, const double *b, double *out, void *stream)
 int pg_cocg_step(int64_t n, int k, const double *alpha2, const double *P, const double *Q, const double *dinv,
                  double *X, double *R, double *Z, double *out, void *work, void *stream);
 
+/* CUDA graph of a batch of the calls above (the launches of the Krylov iterations between two host
+ * checks of the residual): begin capture on a NON-default stream, issue the calls, end -> executable
+ * graph, launch it any number of times. */
+int pg_graph_begin(void *stream);
+int pg_graph_end(void *stream, void **graph_exec);
+int pg_graph_launch(void *graph_exec, void *stream);
+void pg_graph_destroy(void *graph_exec);
+
 #ifdef __cplusplus
 }
 #endif

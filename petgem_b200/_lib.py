@@ -109,6 +109,10 @@ SIGNATURES = {
     "pg_zbdotu": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p]),
     "pg_zbnrm2sq": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbdiv": (C.c_int, [_i32, _p, _p, _p, _p]),
+    "pg_graph_begin": (C.c_int, [_p]),
+    "pg_graph_end": (C.c_int, [_p, C.POINTER(_p)]),
+    "pg_graph_launch": (C.c_int, [_p, _p]),
+    "pg_graph_destroy": (None, [_p]),
     "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

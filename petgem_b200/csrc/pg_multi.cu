@@ -355,4 +355,37 @@ int pg_zbdiv(int k, const double *a, const double *b, double *out, void *stream)
     return PG_OK;
 }
 
+// ---- CUDA graph of a batch of launches -----------------------------------------------------------
+// The Krylov drivers issue ~10 small launches per iteration; between two host checks of the residual
+// nothing depends on the host, so the batch is captured once and replayed (stream must not be the
+// legacy default stream).
+int pg_graph_begin(void *stream) {
+    PG_REQUIRE(stream, PG_EINVAL, "pg_graph_begin: capture needs a non-default stream");
+    PG_CUDA_OK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return PG_OK;
+}
+
+int pg_graph_end(void *stream, void **graph_exec) {
+    PG_REQUIRE(stream && graph_exec, PG_EINVAL, "pg_graph_end: null pointer");
+    cudaGraph_t g = nullptr;
+    *graph_exec = nullptr;
+    PG_CUDA_OK(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    PG_CUDA_OK(e);
+    *graph_exec = ge;
+    return PG_OK;
+}
+
+int pg_graph_launch(void *graph_exec, void *stream) {
+    PG_REQUIRE(graph_exec, PG_EINVAL, "pg_graph_launch: null graph");
+    PG_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return PG_OK;
+}
+
+void pg_graph_destroy(void *graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+}
+
 }  // extern "C"

@@ -12,6 +12,7 @@ all-gathered over NCCL and the dot products are all-reduced.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -166,6 +167,9 @@ class Operator:
     def matmat(self, X: torch.Tensor, Y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
         """Y = A X for k interleaved right-hand sides (X, Y: [n, k]); one pass over the matrix."""
         k = int(X.shape[1])
+        if k == 1:  # an [n, 1] block is a vector: every halo mode applies
+            self.matvec(X.reshape(-1), Y.reshape(-1), row_scale)
+            return Y
         if self.mode == "p2p":
             if getattr(self, "_mm", None) is None or self._mm[0] != k:
                 dev = X.device
@@ -470,55 +474,15 @@ def cocg(op: Operator, b: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50, moni
     """Conjugate-orthogonal CG for the complex SYMMETRIC system (KSPCG with -ksp_cg_type symmetric):
     one SpMV, two unconjugated dots and three vector updates per iteration, no restart.  Jacobi enters
     symmetrically through z = D^-1 r; convergence is tested on the preconditioned residual like PETSc.
-    All coefficients (alpha = rho / p^T A p, beta = rho' / rho) are formed on the device (pg_zdiv), so
-    the host synchronises only every `check_every` iterations to read the residual norm; the returned
-    iteration count is therefore rounded up to that granularity."""
-    n, dev = op.n, b.device
-    vk = VecKernels(n, dev, op.ctx, kmax=4)
-    z_ = lambda: torch.zeros((n,), dtype=_C128, device=dev)  # noqa: E731
-    x, r, z, p_, q = z_(), b.clone(), z_(), z_(), z_()
-    # device scalars: [0] rho  [1] rho_new  [2] p^T A p  [3] alpha  [4] -alpha  [5] beta  [6] -beta  [7] |z|^2
-    sc = torch.zeros((8,), dtype=_C128, device=dev)
-    zdiv = lib().pg_zdiv
-
-    op.precond(r, z)
-    bnorm = math.sqrt(vk.nrm2sq(z, sc[7:8])[0].real.item())
-    if bnorm == 0.0:
-        return SolveResult(x, 0, [0.0], True, "zero rhs")
-    tol = max(rtol * bnorm, atol)
-    p_.copy_(z)
-    vk.dotu(r, z, sc[0:1])
-    hist = [bnorm]
-    it = 0
-    rho_i, rho_new_i = 0, 1
-    import time as _time
-    t_start = _time.time()
-    while it < maxit:
-        for _ in range(min(check_every, maxit - it)):
-            op.matvec(p_, q)
-            vk.dotu(p_, q, sc[2:3])
-            check(zdiv(ptr(sc[rho_i:rho_i + 1]), ptr(sc[2:3]), 0, ptr(sc[3:5]), stream_ptr()), "pg_zdiv")
-            vk.axpy(sc[3:4], p_, x)          # x += alpha p
-            vk.axpy(sc[4:5], q, r)           # r -= alpha A p
-            op.precond(r, z)
-            vk.dotu(r, z, sc[rho_new_i:rho_new_i + 1])
-            check(zdiv(ptr(sc[rho_new_i:rho_new_i + 1]), ptr(sc[rho_i:rho_i + 1]), 0, ptr(sc[5:7]), stream_ptr()),
-                  "pg_zdiv")
-            vk.aypx(sc[5:6], z, p_)          # p = z + beta p
-            rho_i, rho_new_i = rho_new_i, rho_i
-            it += 1
-        res2 = vk.nrm2sq(z, sc[7:8])[0].real.item()  # the host sync of this batch
-        if not math.isfinite(res2):
-            return SolveResult(x, it, hist, False, "breakdown")
-        res = math.sqrt(res2)
-        hist.append(res)
-        if monitor:
-            monitor(it, res)
-        if res <= tol:
-            return SolveResult(x, it, hist, True, "rtol")
-        if max_seconds is not None and _time.time() - t_start > max_seconds:
-            return SolveResult(x, it, hist, False, "time limit")
-    return SolveResult(x, maxit, hist, False, "maxit")
+    All coefficients (alpha = rho / p^T A p, beta = rho' / rho) are formed on the device, so the host
+    synchronises only every `check_every` iterations to read the residual norm; the returned iteration
+    count is therefore rounded up to that granularity.  This is cocg_multi with one right-hand side: per
+    iteration the SpMV, one dot, the fused update/Jacobi/reduction pass and one AYPX."""
+    mon = (lambda it, res: monitor(it, float(res[0]))) if monitor else None
+    r = cocg_multi(op, b.reshape(-1, 1), rtol=rtol, maxit=maxit, atol=atol, monitor=mon, check_every=check_every,
+                   max_seconds=max_seconds)
+    return SolveResult(r.x.reshape(-1), r.iterations, [float(h[0]) for h in r.residuals], bool(r.converged[0]),
+                       r.reason)
 
 
 class MultiSolveResult:
@@ -571,10 +535,12 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
     hist = [bnorm.copy()]
     if not (bnorm > 0).any():
         return MultiSolveResult(X, 0, hist, np.ones(k, dtype=bool), "zero rhs")
-    it, cur = 0, 0
+    it = 0
     t_start = _time.time()
-    while it < maxit:
-        for _ in range(min(check_every, maxit - it)):
+
+    def iterations(count):
+        cur = 0  # count is even, or the last batch: rho[0] is the current rho on entry and on exit
+        for _ in range(count):
             op.matmat(P, Q)
             check(L.pg_zbdotu(n, k, ptr(P), ptr(Q), ptr(pq), ptr(work), st()), "pg_zbdotu")
             reduce_(pq)
@@ -586,20 +552,62 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
             check(L.pg_zbdiv(k, ptr(rho[cur ^ 1]), ptr(rho[cur]), ptr(beta2), st()), "pg_zbdiv")
             check(L.pg_zbaypx(n, k, ptr(beta2), ptr(Z), ptr(P), st()), "pg_zbaypx")
             cur ^= 1
-            it += 1
-        res2 = out2[k:].real.cpu().numpy()  # the host sync of this batch
-        if not np.isfinite(res2).all():
-            return MultiSolveResult(X, it, hist, np.zeros(k, dtype=bool), "breakdown")
-        res = np.sqrt(res2)
-        hist.append(res)
-        if monitor:
-            monitor(it, res)
-        done = res <= tol
-        if done.all():
-            return MultiSolveResult(X, it, hist, done, "rtol")
-        if max_seconds is not None and _time.time() - t_start > max_seconds:
-            return MultiSolveResult(X, it, hist, done, "time limit")
-    return MultiSolveResult(X, maxit, hist, hist[-1] <= tol, "maxit")
+        if cur:
+            rho[0].copy_(rho[1])
+
+    # Single GPU: the `check_every` iterations between two host checks are one CUDA graph (no host work;
+    # the ~10 launches per iteration otherwise dominate small systems).  Capture needs a non-default
+    # stream, so the solve runs on a side stream; PG_CUDA_GRAPH=0 launches eagerly.
+    import ctypes as _C
+
+    gexec = _C.c_void_p()
+    side = None
+    first = False
+    if ctx is None and check_every > 0 and os.environ.get("PG_CUDA_GRAPH", "1") == "1" and maxit >= 2 * check_every:
+        main_stream = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main_stream)
+        torch.cuda.set_stream(side)
+    try:
+        if side is not None:
+            iterations(check_every)  # warm-up outside the capture (counts as iterations)
+            it += check_every
+            first = True
+            if L.pg_graph_begin(st()) == 0:
+                try:
+                    iterations(check_every)
+                finally:
+                    if L.pg_graph_end(st(), _C.byref(gexec)) != 0:
+                        gexec = _C.c_void_p()
+        while it < maxit:
+            if first:
+                first = False  # the warm-up batch is checked before the first replay
+            else:
+                count = min(check_every, maxit - it)
+                if gexec and count == check_every:
+                    check(L.pg_graph_launch(gexec, st()), "pg_graph_launch")
+                else:
+                    iterations(count)
+                it += count
+            res2 = out2[k:].real.cpu().numpy()  # the host sync of this batch
+            if not np.isfinite(res2).all():
+                return MultiSolveResult(X, it, hist, np.zeros(k, dtype=bool), "breakdown")
+            res = np.sqrt(res2)
+            hist.append(res)
+            if monitor:
+                monitor(it, res)
+            done = res <= tol
+            if done.all():
+                return MultiSolveResult(X, it, hist, done, "rtol")
+            if max_seconds is not None and _time.time() - t_start > max_seconds:
+                return MultiSolveResult(X, it, hist, done, "time limit")
+        return MultiSolveResult(X, maxit, hist, hist[-1] <= tol, "maxit")
+    finally:
+        if gexec:
+            L.pg_graph_destroy(gexec)
+        if side is not None:
+            torch.cuda.set_stream(main_stream)
+            main_stream.wait_stream(side)
 
 
 def solve_multi(A: CSRMatrix, B: torch.Tensor, options=None, ctx: DistContext = None, monitor=None):
