@@ -190,24 +190,38 @@ class Solver():
         perm = self.A.perm.to(torch.int64) if self.A.perm is not None else None
         ctx = krylov.DistContext(self.row_begins, self.plan.N) if parEnv.num_proc > 1 else None
         lo, hi = self.plan.row_begin, self.plan.row_begin + self.plan.local_rows
-        for i in np.arange(num_polarizations):
-            b = self.b[i].t
-            if perm is not None:
-                bi = torch.empty_like(b)
-                bi[perm] = b
-            else:
-                bi = b
-            res = krylov.solve(self.A.csr, bi[lo:hi].contiguous(), self.petsc_options, ctx=ctx)  # solver.py:589
-            self.ksp_results.append(res)
-            xi = res.x
+
+        def to_internal(b):
+            if perm is None:
+                return b
+            bi = torch.empty_like(b)
+            bi[perm] = b
+            return bi
+
+        def collect(xi):
             if ctx is not None:  # collect the owned blocks into the replicated solution vector
                 send = torch.zeros((ctx.max_rows,), dtype=torch.complex128, device=xi.device)
                 full = torch.zeros((ctx.world * ctx.max_rows,), dtype=torch.complex128, device=xi.device)
                 ctx.gather(xi, send, full)
                 xi = torch.cat([full[r * ctx.max_rows:r * ctx.max_rows + ctx.sizes[r]] for r in range(ctx.world)])
-            self.x[i].t.copy_(xi[perm] if perm is not None else xi)
+            return xi[perm] if perm is not None else xi
+
+        if num_polarizations > 1:
+            # the right-hand sides share A (the two MT polarizations): one pass over the matrix per
+            # iteration for all of them when the solver type allows it (krylov.solve_multi)
+            B = torch.stack([to_internal(self.b[i].t)[lo:hi] for i in np.arange(num_polarizations)], dim=1).contiguous()
+            X, results = krylov.solve_multi(self.A.csr, B, self.petsc_options, ctx=ctx)   # solver.py:589
+            self.ksp_results = list(results)
+            xs = [X[:, i].contiguous() for i in range(num_polarizations)]
+        else:
+            res = krylov.solve(self.A.csr, to_internal(self.b[0].t)[lo:hi].contiguous(), self.petsc_options,
+                               ctx=ctx)                                                     # solver.py:589
+            self.ksp_results.append(res)
             if not res.converged:
                 Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
+            xs = [res.x]
+        for i in np.arange(num_polarizations):
+            self.x[i].t.copy_(collect(xs[i]))
             if parEnv.rank == 0:
                 writePetscVector(out_dir + '/x' + str(i) + '.dat', self.x[i])
         torch.cuda.synchronize()
