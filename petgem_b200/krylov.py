@@ -1,4 +1,4 @@
-"""Krylov drivers (restarted GMRES, BiCGStab) over the C-ABI vector kernels.
+"""Krylov drivers (restarted GMRES, BiCGStab, TFQMR, COCG) over the C-ABI vector kernels.
 
 Stands in for ``ksp.solve(b, x)`` at ``petgem/solver.py:584-590`` with the PETSc
 defaults that apply silently there: GMRES restart 30, LEFT
@@ -6,8 +6,11 @@ preconditioning, classical Gram-Schmidt (one VecMDot + one VecMAXPY per
 iteration), zero initial guess, convergence on the preconditioned residual norm
 relative to ||M^-1 b||, maxit 10000.  Host code is Python; every vector operation
 is a kernel from include/petgem_b200.h working on device scalars.  With a process
-group, rows are owned PETSc-style by contiguous blocks: the SpMV input is
-all-gathered over NCCL and the dot products are all-reduced.
+group, rows are owned PETSc-style by contiguous blocks: before the SpMV the x halo
+is exchanged over NCCL (packed neighbour entries, all-gather as the fallback) and
+the dot products are all-reduced.  Right-hand sides that share A (several sources,
+the MT polarizations) advance in lockstep through ``solve_multi`` / ``cocg_multi``:
+interleaved [n, k] blocks, one pass over the matrix per iteration for all k.
 """
 from __future__ import annotations
 
