@@ -6,6 +6,8 @@
 // 17 B per nonzero instead of 20, half the x gathers, a third of the load instructions.
 // Same arithmetic order per row as the CSR kernel up to the lane assignment; MatMult semantics
 // (solver.py:589, inside KSP).
+#include <stdlib.h>
+
 #include "pg_plan.cuh"
 
 namespace pg {
@@ -25,13 +27,18 @@ __global__ void __launch_bounds__(256, 6) spmv_blocked2_kernel(int64_t nb, const
                                                                const double2 *__restrict__ vals,
                                                                const double2 *__restrict__ x,
                                                                const double2 *__restrict__ dscale,
-                                                               double2 *__restrict__ y) {
+                                                               double2 *__restrict__ y, int chunk) {
     const int lane = threadIdx.x % kBG;
-    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kBG;
-    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / kBG;
+    // In-order grid: block b takes the `chunk` consecutive tiles of 32 entities starting at b*chunk, so a
+    // single front moves through the matrix and the x entries shared by neighbouring rows are still in
+    // L2 when they are needed again (a capped grid-stride launch runs ~12 interleaved sweeps instead:
+    // measured at C3, SpMV 6.17 -> 5.19 ms, four right-hand sides 10.8 -> 9.2 ms).
+    const int gpb = blockDim.x / kBG;
     const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
     const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
-    for (int64_t i = grp; i < nb; i += ngrp) {
+    for (int c = 0; c < chunk; ++c) {
+        const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
+        if (i >= nb) break;
         const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
         const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
         const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
@@ -98,16 +105,17 @@ __global__ void __launch_bounds__(256) spmm_blocked2_kernel(int64_t nb, const En
                                                             const double2 *__restrict__ vals,
                                                             const double2 *__restrict__ X,
                                                             const double2 *__restrict__ dscale,
-                                                            double2 *__restrict__ Y) {
+                                                            double2 *__restrict__ Y, int chunk) {
     constexpr int NS = kBG / K;  // column entities per step of a group
     const int lane = threadIdx.x % kBG;
     const int r = lane % K, sub = lane / K;
-    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kBG;
-    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / kBG;
+    const int gpb = blockDim.x / kBG;  // in-order grid, see spmv_blocked2_kernel
     const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
     const uint64_t stream = l2_policy_evict_first();
     const double2 *Xr = X + r;
-    for (int64_t i = grp; i < nb; i += ngrp) {
+    for (int c = 0; c < chunk; ++c) {
+        const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
+        if (i >= nb) break;
         const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
         const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
         const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
@@ -173,13 +181,14 @@ __global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, con
                                                                  const double2 *__restrict__ vals,
                                                                  const double2 *__restrict__ X,
                                                                  const double2 *__restrict__ dscale,
-                                                                 double2 *__restrict__ Y) {
+                                                                 double2 *__restrict__ Y, int chunk) {
     const int lane = threadIdx.x % kBG;
-    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kBG;
-    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / kBG;
+    const int gpb = blockDim.x / kBG;  // in-order grid, see spmv_blocked2_kernel
     const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
     const uint64_t stream = l2_policy_evict_first();
-    for (int64_t i = grp; i < nb; i += ngrp) {
+    for (int c = 0; c < chunk; ++c) {
+        const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
+        if (i >= nb) break;
         const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
         const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
         const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
@@ -245,16 +254,17 @@ extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const
     PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmv_blocked: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
     const int64_t nb = pl->b1 - pl->b0;
     if (nb == 0) return PG_OK;
-    const int64_t blocks = std::min<int64_t>((nb * kBG + 255) / 256, (int64_t)kNumSMs * 96);
+    const int chunk = 1;
+    const int64_t tiles = (nb * kBG + 255) / 256, blocks = (tiles + chunk - 1) / chunk;
     const int32_t *cs = colstart ? colstart : pl->colstart;
     const double2 *v2 = reinterpret_cast<const double2 *>(vals), *x2 = reinterpret_cast<const double2 *>(x);
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(y);
     cudaStream_t st = (cudaStream_t)stream;
     switch (spmv_hint_mode()) {
-        case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
-        case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
-        default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2);
+        case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
     return PG_OK;
@@ -267,16 +277,21 @@ extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const
     PG_REQUIRE(k == 2 || k == 4 || k == 8, PG_EINVAL, "pg_spmm_blocked: k = %d (2, 4 or 8)", k);
     const int64_t nb = pl->b1 - pl->b0;
     if (nb == 0) return PG_OK;
-    const int64_t blocks = std::min<int64_t>((nb * kBG + 255) / 256, (int64_t)kNumSMs * 96);
+    static const int chunk_env = [] {
+        const char *e = getenv("PG_SPMM_CHUNK");
+        return e ? atoi(e) : 0;
+    }();
+    const int chunk = chunk_env > 0 ? chunk_env : 4;
+    const int64_t tiles = (nb * kBG + 255) / 256, blocks = (tiles + chunk - 1) / chunk;
     const int32_t *cs = colstart ? colstart : pl->colstart;
     const double2 *v2 = reinterpret_cast<const double2 *>(vals), *x2 = reinterpret_cast<const double2 *>(X);
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(Y);
     cudaStream_t st = (cudaStream_t)stream;
     switch (k) {
-        case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
-        case 4: spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2); break;
-        default: spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2);
+        case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 4: spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        default: spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
     return PG_OK;

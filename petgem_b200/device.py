@@ -283,13 +283,13 @@ class CSRMatrix:
         self.N, self.row_begin = int(N), int(row_begin)
         self.rows = int(rowptr.numel() - 1)
         self.nnz = int(vals.numel())
-        # with the plan that produced vals (p = 2) MatMult can use the entity-blocked kernel: the plan's
-        # per-entity column lists replace colidx (17 B per nonzero instead of 20).  Measured on B200
-        # (tools/spmv_bench.py): +5 % at 1.6 M tets, -3 % at 5 M tets against the CSR kernel -- the SpMV is
-        # latency- rather than byte-bound there -- so it is opt-in (blocked=True or PG_SPMV_BLOCKED=1).
+        # with the plan that produced vals (p = 2) MatMult uses the entity-blocked kernel: the plan's
+        # per-entity column lists replace colidx (17 B per nonzero instead of 20, half the x gathers).
+        # Measured on B200 at C3 (tools/spmv_bench.py) with the in-order grid: 5.19 ms against 5.96 ms for
+        # the CSR kernel.  blocked=False or PG_SPMV_BLOCKED=0 selects the CSR kernel.
         import os
         if blocked is None:
-            blocked = os.environ.get("PG_SPMV_BLOCKED", "0") == "1"
+            blocked = os.environ.get("PG_SPMV_BLOCKED", "1") == "1"
         self.plan_ref = plan if (plan is not None and plan.p == 2) else None  # entity blocks of this matrix
         self.plan = self.plan_ref if blocked else None
         self.colstart = colstart  # None = the plan's own global column starts

@@ -53,6 +53,16 @@ def _worker(rank, world, port, N, cuts, seed, out):
         assert np.array_equal(xbuf.numpy()[col_h.numpy()], x[Aloc.indices])
         Ap = sp.csr_matrix((Aloc.data, col_h.numpy(), Aloc.indptr), shape=(nloc, nloc + next_))
         assert np.abs(Ap @ xbuf.numpy() - (A @ x)[lo:hi]).max() < 1e-12
+        # the same halo for an interleaved block of k right-hand sides (lockstep multi-source solve)
+        from petgem_b200.krylov import _exchange_multi
+
+        for k in (2, 4):
+            Xk = rng.normal(size=(N, k)) + 1j * rng.normal(size=(N, k))
+            sb = torch.zeros((int(sum(send_splits)), k), dtype=torch.complex128)
+            xb = torch.zeros((nloc + next_, k), dtype=torch.complex128)
+            _exchange_multi(ctx, torch.from_numpy(Xk[lo:hi].copy()), send_idx, send_splits, recv_splits, sb, xb)
+            assert np.array_equal(xb.numpy()[col_h.numpy()], Xk[Aloc.indices])
+            assert np.abs(Ap @ xb.numpy() - (A @ Xk)[lo:hi]).max() < 1e-12
         # all-reduced dot product equals the global one
         d = torch.tensor([np.vdot(x[lo:hi], y)], dtype=torch.complex128)
         ctx.allreduce(d)

@@ -591,8 +591,8 @@ def test_entity_blocked_spmv_equals_csr(topo, order):
     assert torch.linalg.vector_norm(yb - Acsr.mult(x)[cut:]) <= 1e-14 * torch.linalg.vector_norm(yb)
     # several right-hand sides: blocked SpMM (k lanes per block / lane per block) == CSR SpMM == k SpMVs
     Apart = CSRMatrix(rp2, ci2, v2, plan.N, part.row_begin, plan=part)
-    Aref_ = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan)
-    assert Aref_.plan is None and Aref_.plan_ref is plan
+    Aref_ = CSRMatrix(rowptr, colidx, vals, plan.N, plan=plan, blocked=False)
+    assert Aref_.plan is None and Aref_.plan_ref is plan  # CSR SpMV, entity-blocked SpMM
     for k in (2, 4, 8):
         X = torch.randn((plan.N, k), dtype=torch.complex128, generator=gen).to(vals.device)
         Yc, Yb = Acsr.mult_multi(X), Aref_.mult_multi(X)
