@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--m", type=int, default=94, help="hexes per box side (T = 6 m^3); 94 = C3")
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--solve-maxit", type=int, default=20000)
+    ap.add_argument("--solve-maxit", type=int, default=40000)
     ap.add_argument("--solve-seconds", type=float, default=75.0, help="wall-time bound of the C3 solve")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
