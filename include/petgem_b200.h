@@ -247,6 +247,15 @@ int pg_zbaypx(int64_t n, int k, const double *beta, const double *X, double *Y, 
 int pg_zbscale_rows(int64_t n, int k, const double *d, const double *X, double *Y, void *stream);
 /* out[r] = sum_i X[i,r] Y[i,r] (no conjugation) */
 int pg_zbdotu(int64_t n, int k, const double *X, const double *Y, double *out, void *work, void *stream);
+/* out[r] = sum_i X[i,r] w[i] Y[i,r] (no conjugation; w NULL: no weight) */
+int pg_zbdotu_w(int64_t n, int k, const double *X, const double *Y, const double *w, double *out, void *work,
+                void *stream);
+/* COCR, the element-wise passes of an iteration: X += alpha P, RT -= alpha dinv .* AP (alpha2 = {alpha[k],
+ * -alpha[k]}, dinv NULL: no preconditioner) and P = RT + beta P, AP = ART + beta AP */
+int pg_cocr_update(int64_t n, int k, const double *alpha2, const double *P, const double *AP, const double *dinv,
+                   double *X, double *RT, void *stream);
+int pg_cocr_direction(int64_t n, int k, const double *beta, const double *RT, const double *ART, double *P,
+                      double *AP, void *stream);
 /* out[r] = sum_i |X[i,r]|^2 */
 int pg_zbnrm2sq(int64_t n, int k, const double *X, double *out, void *work, void *stream);
 /* out[r] = a[r] / b[r] (0 where b[r] == 0), out[k + r] = -out[r] */

@@ -107,6 +107,9 @@ SIGNATURES = {
     "pg_zbaypx": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbscale_rows": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbdotu": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p]),
+    "pg_zbdotu_w": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "pg_cocr_update": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "pg_cocr_direction": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
     "pg_zbnrm2sq": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbdiv": (C.c_int, [_i32, _p, _p, _p, _p]),
     "pg_graph_begin": (C.c_int, [_p]),

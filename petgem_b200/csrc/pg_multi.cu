@@ -172,16 +172,18 @@ __global__ void __launch_bounds__(kRedThreadsM) reduce_stage2_m(const double2 *_
     }
 }
 
-// out[r] = sum_i X[i,r] Y[i,r] (unconjugated), or sum |X[i,r]|^2 when Y == nullptr
+// out[r] = sum_i X[i,r] w[i] Y[i,r] (unconjugated; w == nullptr: no weight), or sum |X[i,r]|^2 when
+// Y == nullptr
 template <int K>
 __global__ void __launch_bounds__(kRedThreadsM) zbdot_stage1(int64_t ntot, const double2 *__restrict__ X,
                                                              const double2 *__restrict__ Y,
+                                                             const double2 *__restrict__ w,
                                                              double2 *__restrict__ partial) {
     double2 acc[1] = {make_double2(0.0, 0.0)};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ntot; i += (int64_t)gridDim.x * blockDim.x) {
         const double2 x = X[i];
         if (Y) {
-            mcfma(acc[0], x, Y[i]);
+            mcfma(acc[0], x, w ? mcmul(__ldg(w + i / K), Y[i]) : Y[i]);
         } else {
             acc[0].x = fma(x.x, x.x, acc[0].x);
             acc[0].x = fma(x.y, x.y, acc[0].x);
@@ -216,6 +218,43 @@ __global__ void __launch_bounds__(kRedThreadsM) cocg_step_kernel(int64_t ntot, c
         acc[1].x = fma(z.y, z.y, acc[1].x);
     }
     block_reduce_store_rhs<K, 2>(acc, partial);
+}
+
+// COCR (conjugate-orthogonal conjugate residuals), the two element-wise passes of an iteration:
+//   update:    X += alpha P,  RT -= alpha dinv .* AP        (RT = M^-1 r, the preconditioned residual)
+//   direction: P = RT + beta P,  AP = ART + beta AP         (ART = A RT from the SpMV in between)
+template <int K>
+__global__ void __launch_bounds__(256) cocr_update_kernel(int64_t ntot, const double2 *__restrict__ alpha2,
+                                                          const double2 *__restrict__ P,
+                                                          const double2 *__restrict__ AP,
+                                                          const double2 *__restrict__ dinv, double2 *__restrict__ X,
+                                                          double2 *__restrict__ RT) {
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double2 al = alpha2[i0 & (K - 1)], nal = alpha2[K + (i0 & (K - 1))];
+    for (int64_t i = i0; i < ntot; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 x = X[i], r = RT[i];
+        const double2 ap = AP[i];
+        mcfma(x, al, P[i]);
+        mcfma(r, nal, dinv ? mcmul(__ldg(dinv + i / K), ap) : ap);
+        X[i] = x;
+        RT[i] = r;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) cocr_direction_kernel(int64_t ntot, const double2 *__restrict__ beta,
+                                                             const double2 *__restrict__ RT,
+                                                             const double2 *__restrict__ ART,
+                                                             double2 *__restrict__ P, double2 *__restrict__ AP) {
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double2 be = beta[i0 & (K - 1)];
+    for (int64_t i = i0; i < ntot; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = RT[i], ap = ART[i];
+        mcfma(p, be, P[i]);
+        mcfma(ap, be, AP[i]);
+        P[i] = p;
+        AP[i] = ap;
+    }
 }
 
 // out[r] = a[r] / b[r] (0 when b[r] == 0: an all-zero right-hand side stays zero), out[K + r] = -out[r]
@@ -311,7 +350,7 @@ int pg_zbdotu(int64_t n, int k, const double *X, const double *Y, double *out, v
     PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_zbdotu: bad size");
     PG_REQUIRE(X && Y && out && work, PG_EINVAL, "pg_zbdotu: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(KK) zbdot_stage1<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(X), CD2(Y), D2(work))
+#define CALL(KK) zbdot_stage1<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(X), CD2(Y), nullptr, D2(work))
     PG_K_SWITCH(k, CALL)
 #undef CALL
     PG_LAUNCH_OK();
@@ -320,11 +359,51 @@ int pg_zbdotu(int64_t n, int k, const double *X, const double *Y, double *out, v
     return PG_OK;
 }
 
+int pg_zbdotu_w(int64_t n, int k, const double *X, const double *Y, const double *w, double *out, void *work,
+                void *stream) {
+    PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_zbdotu_w: bad size");
+    PG_REQUIRE(X && Y && out && work, PG_EINVAL, "pg_zbdotu_w: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KK) zbdot_stage1<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(X), CD2(Y), CD2(w), D2(work))
+    PG_K_SWITCH(k, CALL)
+#undef CALL
+    PG_LAUNCH_OK();
+    reduce_stage2_m<<<k, kRedThreadsM, 0, st>>>(CD2(work), D2(out));
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int pg_cocr_update(int64_t n, int k, const double *alpha2, const double *P, const double *AP, const double *dinv,
+                   double *X, double *RT, void *stream) {
+    PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_cocr_update: bad size");
+    if (n == 0) return PG_OK;
+    PG_REQUIRE(alpha2 && P && AP && X && RT, PG_EINVAL, "pg_cocr_update: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KK) cocr_update_kernel<KK><<<ew_blocks(n * k), 256, 0, st>>>(n * k, CD2(alpha2), CD2(P), CD2(AP), CD2(dinv), D2(X), D2(RT))
+    PG_K_SWITCH(k, CALL)
+#undef CALL
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int pg_cocr_direction(int64_t n, int k, const double *beta, const double *RT, const double *ART, double *P,
+                      double *AP, void *stream) {
+    PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_cocr_direction: bad size");
+    if (n == 0) return PG_OK;
+    PG_REQUIRE(beta && RT && ART && P && AP, PG_EINVAL, "pg_cocr_direction: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KK) cocr_direction_kernel<KK><<<ew_blocks(n * k), 256, 0, st>>>(n * k, CD2(beta), CD2(RT), CD2(ART), D2(P), D2(AP))
+    PG_K_SWITCH(k, CALL)
+#undef CALL
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
 int pg_zbnrm2sq(int64_t n, int k, const double *X, double *out, void *work, void *stream) {
     PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_zbnrm2sq: bad size");
     PG_REQUIRE(X && out && work, PG_EINVAL, "pg_zbnrm2sq: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(KK) zbdot_stage1<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(X), nullptr, D2(work))
+#define CALL(KK) zbdot_stage1<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(X), nullptr, nullptr, D2(work))
     PG_K_SWITCH(k, CALL)
 #undef CALL
     PG_LAUNCH_OK();

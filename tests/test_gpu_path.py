@@ -719,6 +719,13 @@ def test_lockstep_multi_source_solve_matches_single(topo, oracle):
         assert single.converged
         assert np.linalg.norm(Xh[:, r] - single.x.cpu().numpy()) <= 1e-8 * np.linalg.norm(xd)
     assert not Xh[:, 2].any()  # the zero right-hand side stays exactly zero
+    # conjugate-orthogonal conjugate residuals (-ksp_type cr): same systems, same answers, fewer iterations
+    Xr, resr = krylov.solve_multi(A, Bd, dict(opts, ksp_type="cr"))
+    assert resr[0].converged.all(), (resr[0].reason, resr[0].residuals[-1])
+    assert np.linalg.norm(Xr.cpu().numpy() - Xh) <= 1e-8 * np.linalg.norm(Xh)
+    assert resr[0].iterations <= results[0].iterations
+    single = krylov.solve(A, Bd[:, 0].contiguous(), dict(opts, ksp_type="cr"))
+    assert single.converged and np.linalg.norm(single.x.cpu().numpy() - Xh[:, 0]) <= 1e-8 * np.linalg.norm(Xh[:, 0])
     # other solver types fall back to one solve per right-hand side, same answers
     Xg, resg = krylov.solve_multi(A, Bd[:, :2].contiguous(), {"ksp_type": "gmres", "pc_type": "jacobi",
                                                                "ksp_rtol": 1e-12, "ksp_max_it": 20000})
