@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--solve-maxit", type=int, default=40000)
-    ap.add_argument("--solve-seconds", type=float, default=75.0, help="wall-time bound of the C3 solve")
+    ap.add_argument("--solve-seconds", type=float, default=120.0, help="wall-time bound of the C3 solve")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-tts", action="store_true")
     ap.add_argument("--tts-m", type=int, default=55, help="box size of the time-to-solution case (55 = C2)")
