@@ -503,6 +503,63 @@ def bicgstab(matvec, b, rtol=1e-8, maxit=10000, pc=None):
     return x, maxit, hist
 
 
+def cocg(matvec, b, rtol=1e-8, maxit=10000, dinv=None):
+    """Conjugate-orthogonal CG for a complex SYMMETRIC matrix (van der Vorst & Melissen 1990; what
+    `-ksp_type cg -ksp_cg_type symmetric` runs in PETSc): CG with the unconjugated bilinear form x^T y,
+    symmetric Jacobi through z = dinv * r, convergence on ||z|| / ||dinv * b||."""
+    d = np.ones_like(b) if dinv is None else dinv
+    x = np.zeros_like(b, dtype=np.complex128)
+    r = b.astype(np.complex128).copy()
+    z = d * r
+    p_ = z.copy()
+    rho = r @ z
+    bnorm = np.linalg.norm(z)
+    hist = [bnorm]
+    for it in range(1, maxit + 1):
+        q = matvec(p_)
+        alpha = rho / (p_ @ q)
+        x = x + alpha * p_
+        r = r - alpha * q
+        z = d * r
+        rho_new = r @ z
+        p_ = z + (rho_new / rho) * p_
+        rho = rho_new
+        hist.append(np.linalg.norm(z))
+        if hist[-1] <= rtol * bnorm:
+            return x, it, hist
+    return x, maxit, hist
+
+
+def cocr(matvec, b, rtol=1e-8, maxit=10000, dinv=None):
+    """Conjugate-orthogonal conjugate residuals for a complex symmetric matrix (Sogabe & Zhang 2007,
+    preconditioned form): recurrences on rt = dinv * r with the unconjugated bilinear form; one matvec per
+    iteration (A p is updated by recurrence); convergence on ||rt|| / ||dinv * b||."""
+    d = np.ones_like(b) if dinv is None else dinv
+    x = np.zeros_like(b, dtype=np.complex128)
+    rt = d * b.astype(np.complex128)
+    p_ = rt.copy()
+    art = matvec(rt)
+    ap = art.copy()
+    rho = rt @ art
+    bnorm = np.linalg.norm(rt)
+    hist = [bnorm]
+    for it in range(1, maxit + 1):
+        map_ = d * ap
+        alpha = rho / (ap @ map_)
+        x = x + alpha * p_
+        rt = rt - alpha * map_
+        art = matvec(rt)
+        rho_new = rt @ art
+        beta = rho_new / rho
+        rho = rho_new
+        p_ = rt + beta * p_
+        ap = art + beta * ap
+        hist.append(np.linalg.norm(rt))
+        if hist[-1] <= rtol * bnorm:
+            return x, it, hist
+    return x, maxit, hist
+
+
 # ---------------------------------------------------------------------------
 # CSEM right-hand side and receiver interpolation
 # ---------------------------------------------------------------------------

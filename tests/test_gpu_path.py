@@ -471,6 +471,13 @@ def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
     xo, its_o, _ = oracle.gmres(lambda v: As @ v, b, rtol=1e-8, pc=lambda v: dinv * v)
     res8 = krylov.solve(A, bd, {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-8})
     assert res8.converged and abs(res8.iterations - its_o) <= max(3, its_o // 50), (res8.iterations, its_o)
+    # COCG / COCR: same iteration counts as the oracle's restatements (the GPU count is rounded up to the
+    # 10-iteration host check)
+    for ksp, ref_solver in (("cg", oracle.cocg), ("cr", oracle.cocr)):
+        _, its_ref, _ = ref_solver(lambda v: As @ v, b, rtol=1e-8, maxit=20000, dinv=dinv)
+        r8 = krylov.solve(A, bd, {"ksp_type": ksp, "ksp_cg_type": "symmetric", "pc_type": "jacobi", "ksp_rtol": 1e-8,
+                                  "ksp_max_it": 20000})
+        assert r8.converged and -10 <= r8.iterations - its_ref <= 10 + its_ref // 50, (ksp, r8.iterations, its_ref)
     # A is complex symmetric: -ksp_type cg -ksp_cg_type symmetric (COCG) applies
     resc = krylov.solve(A, bd, {"ksp_type": "cg", "ksp_cg_type": "symmetric", "pc_type": "jacobi",
                                 "ksp_rtol": 1e-12, "ksp_max_it": 20000})
