@@ -154,7 +154,17 @@ class Preprocessing():
                                           edgesNodes[elemsE[srcElem]].reshape(-1), dofs[srcElem]]).astype(np.float64)
             writePetscVector(out_dir + '/source.dat', createSequentialVectorWithArray(data_source))
         else:
-            Print.master('     MT boundary elements (preprocessing.py:314-381) are not produced by petgem_b200')
+            # one row per boundary face with everything the MT right-hand side needs (preprocessing.py:314-381)
+            planeFace = pmesh.computeFacePlane(points, bFaces, bFacesN)
+            bElems, numbElems = pmesh.computeBoundaryElements(elemsF, bFaces, nFaces)
+            if nbFaces != numbElems:
+                Print.master('     Number of boundary faces is not consistent.')
+                exit(-1)
+            data_boundaries = boundary_element_rows(points, cells, elemsE, edgesNodes, elemsF, facesE, dofs,
+                                                    conductivityModel, bFaces, bElems, planeFace)
+            writeParallelDenseMatrix(out_dir + '/boundaryElements.dat',
+                                     createSequentialDenseMatrixWithArray(data_boundaries.shape[0],
+                                                                          data_boundaries.shape[1], data_boundaries))
         valence = np.array([50, 200, 400, 800, 1400, 2500])  # preprocessing.py:470-473
         writePetscVector(out_dir + '/nnz.dat',
                          createSequentialVectorWithArray(np.full(total_num_dofs, valence[p - 1], dtype=np.float64)))
@@ -162,6 +172,28 @@ class Preprocessing():
         np.savez(out_dir + '/mesh_tables.npz', nodes=points, elemsN=cells, elemsE=elemsE, edgesNodes=edgesNodes,
                  elemsF=elemsF, facesE=facesE, dofs=dofs)
         Print.master('     Number of elements: %d, dofs: %d' % (nElems, total_num_dofs))
+
+
+def boundary_element_rows(points, cells, elemsE, edgesNodes, elemsF, facesE, dofs, conductivityModel, bFaces,
+                          bElems, planeFace):
+    """Rows of boundaryElements.dat (preprocessing.py:326-367), one per boundary face: nodes 0:4,
+    coordinates 4:16, faces 16:20, edges of the faces 20:32, edges 32:38, nodes of the edges 38:50, plane
+    flag 50, global face id 51, horizontal sigma 52, dofs 53:."""
+    points, cells = np.asarray(points), np.asarray(cells)
+    t = np.asarray(bElems, dtype=np.int64)
+    nb, n = t.size, np.asarray(dofs).shape[1]
+    rows = np.zeros((nb, 53 + n), dtype=np.float64)
+    rows[:, 0:4] = cells[t]
+    rows[:, 4:16] = points[cells[t]].reshape(nb, 12)
+    rows[:, 16:20] = np.asarray(elemsF)[t]
+    rows[:, 20:32] = np.asarray(facesE)[np.asarray(elemsF)[t]].reshape(nb, 12)
+    rows[:, 32:38] = np.asarray(elemsE)[t]
+    rows[:, 38:50] = np.asarray(edgesNodes)[np.asarray(elemsE)[t]].reshape(nb, 12)
+    rows[:, 50] = planeFace
+    rows[:, 51] = bFaces
+    rows[:, 52] = np.asarray(conductivityModel)[t, 0]
+    rows[:, 53:] = np.asarray(dofs)[t]
+    return rows
 
 
 def unitary_test():

@@ -1,0 +1,57 @@
+"""Fully symmetric quadrature rules on the unit triangle, degrees 2..12 (even).
+
+The reference tabulates "order 2p" rules for the MT boundary integrals
+(``hvfem.compute2DGaussPoints``, hvfem.py:1613-2300, called at solver.py:323-324): the classical
+minimal-point symmetric rules of D. A. Dunavant (Int. J. Numer. Meth. Eng. 21, 1985) with 3, 6, 12,
+16, 25 and 33 points.  The integrand of that boundary term is not polynomial (the 1-D MT field
+varies along z), so unlike the volume rule (``basis.tet_quadrature``) the points themselves matter
+for agreement with the reference.  The orbit parameters below were re-derived, not copied:
+``tools/make_triangle_rules.py`` solves the moment equations for the published orbit structures
+(S3 = centroid, S21(a) = permutations of (a, a, 1-2a), S111(a, b) = permutations of (a, b, 1-a-b));
+``tests/test_host.py`` checks exactness on every monomial up to the degree and
+``tests/test_mt.py`` the agreement with the reference's points (as a set) to 1e-14.
+
+Weights sum to 1/2 (the area of the unit triangle), as in the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# degree -> list of orbits: ("s3", w) | ("s21", w, a) | ("s111", w, a, b)
+_ORBITS = {
+    2: [("s21", 1.0 / 6.0, 1.0 / 6.0)],
+    4: [("s21", 0.054975871827660873, 0.09157621350977066),
+        ("s21", 0.11169079483900581, 0.44594849091596495)],
+    6: [("s21", 0.025422453185101706, 0.063089014491499909),
+        ("s21", 0.058393137863180428, 0.24928674517092173),
+        ("s111", 0.041425537809192274, 0.0531450498448248, 0.31035245103377535)],
+    8: [("s3", 0.072157803838942242),
+        ("s21", 0.04754581713360953, 0.45929258829279074),
+        ("s21", 0.016229248811595157, 0.050547228317029569),
+        ("s21", 0.051608685267356312, 0.17056930775183615),
+        ("s111", 0.013615157087229119, 0.2631128296344189, 0.0083947774100495039)],
+}
+
+
+def triangle_quadrature(degree: int):
+    """Points (xi, eta) [ng, 2] and weights [ng] of the symmetric rule exact for polynomials of the
+    given (even) degree on the triangle (0,0), (1,0), (0,1)."""
+    if degree not in _ORBITS:
+        raise ValueError("triangle_quadrature: degree %r not tabulated (%s)" % (degree, sorted(_ORBITS)))
+    pts, wts = [], []
+    for orbit in _ORBITS[degree]:
+        kind, w = orbit[0], orbit[1]
+        if kind == "s3":
+            bary = [(1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0)]
+        elif kind == "s21":
+            a = orbit[2]
+            c = 1.0 - 2.0 * a
+            bary = [(a, a, c), (a, c, a), (c, a, a)]
+        else:
+            a, b = orbit[2], orbit[3]
+            c = 1.0 - a - b
+            bary = [(a, b, c), (a, c, b), (b, a, c), (b, c, a), (c, a, b), (c, b, a)]
+        for q in bary:
+            pts.append((q[0], q[1]))
+            wts.append(w)
+    return np.array(pts, dtype=np.float64), np.array(wts, dtype=np.float64)

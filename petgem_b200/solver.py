@@ -149,16 +149,19 @@ class Solver():
             rhs_contribution = np.matmul(field, basis[:, :, 0]) * Const
             self.b[0].setValues(dofsSource, rhs_contribution, addv=True)
         elif mode == 'mt':
-            Print.master('     MT boundary right-hand side (solver.py:318-512) is outside the B200 hot path: '
-                         'assemble b with the reference and pass it through b{i}.dat')
-            import os
-            out_dir = inputSetup.output.get('directory_scratch')
-            for i in np.arange(num_polarizations):
-                path = out_dir + '/b' + str(i) + '.dat'
-                if not os.path.exists(path):
-                    Print.master('     missing ' + path)
+            # Neumann excitation from the 1-D layered-earth solution on the box sides (solver.py:318-512):
+            # host numpy on every rank (b is replicated), like the reference's serial loops
+            from . import mt
+            rows = self.boundaries.array.real
+            za, zb = float(self.nodes[:, 2::3].max()), float(self.nodes[:, 2::3].min())  # solver.py:381-401
+            pols = data_model.get('polarization')
+            for tmp in pols:
+                if tmp not in ('x', 'y'):
+                    Print.master('     MT polarization mode not supported.')
                     exit(-1)
-                self.b[i].t.copy_(torch.as_tensor(readPetscVector(path).getArray(), device=self.b[i].t.device))
+            rhs = mt.mt_rhs(rows, za, zb, basis_order, omega, mu, list(pols), self.total_num_dofs)
+            for i in np.arange(num_polarizations):
+                self.b[i].t.copy_(torch.as_tensor(rhs[i], device=self.b[i].t.device))
         for i in np.arange(num_polarizations):
             self.b[i].assemblyBegin()
             self.b[i].assemblyEnd()
