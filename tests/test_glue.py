@@ -201,3 +201,95 @@ def test_kernel_cli_end_to_end(tmp_path, topo, oracle):
     from petgem_b200.parallel import readPetscVector
     x = readPetscVector(str(tmp_path / "tmp" / "x0.dat")).getArray()
     assert np.linalg.norm(x - xd) <= 1e-6 * np.linalg.norm(xd)
+
+
+PARAMS_MT = """
+model:
+  mode: mt
+  mt:
+    sigma:
+      horizontal: [1., 0.01, 1., 3.3333]
+      vertical: [1., 0.01, 1., 3.3333]
+    frequency: 2.
+    polarization: 'xy'
+  mesh: %(mesh)s
+  receivers: %(rec)s
+run:
+  nord: %(nord)d
+  cuda: True
+output:
+  vtk: False
+  directory: %(out)s
+  directory_scratch: %(tmp)s
+"""
+
+
+def make_mt_case(tmp_path, topo, nord=1):
+    params, opts = make_case(tmp_path, topo, nord=nord)
+    with open(params, "w") as fh:
+        fh.write(PARAMS_MT % dict(mesh=str(tmp_path / "case.msh"), rec=str(tmp_path / "receivers.npy"), nord=nord,
+                                  out=str(tmp_path / "out"), tmp=str(tmp_path / "tmp")))
+    with open(opts, "w") as fh:
+        fh.write("-ksp_type cr\n-pc_type jacobi\n-ksp_rtol 1e-9\n-ksp_max_it 40000\n")
+    return params, opts
+
+
+def test_mt_preprocessing_writes_boundary_elements(tmp_path, topo):
+    """mode: mt -> boundaryElements.dat with the reference's row layout (preprocessing.py:326-381)."""
+    from petgem_b200 import parallel as par
+    from petgem_b200.common import InputParameters
+    from petgem_b200.preprocessing import Preprocessing
+
+    params, _ = make_mt_case(tmp_path, topo, nord=2)
+    setup = InputParameters(params)
+    assert setup.run["num_polarizations"] == 2
+    Preprocessing().run(setup)
+    tmp = setup.output["directory_scratch"]
+    rows = par.readPetscMatrix(tmp + "/boundaryElements.dat").array.real
+    gold = golden("mt_rhs.npz")
+    nb = gold["bElems"].size
+    assert rows.shape == (nb, 53 + 20)
+    t = gold["bElems"].astype(np.int64)
+    assert np.array_equal(rows[:, 0:4].astype(np.int64), topo["elemsN"][t])
+    assert np.array_equal(rows[:, 4:16], topo["nodes"][topo["elemsN"][t]].reshape(nb, 12))
+    assert np.array_equal(rows[:, 16:20].astype(np.int64), topo["elemsF"][t])
+    assert np.array_equal(rows[:, 50].astype(np.int64), gold["planeFace"])
+    assert np.array_equal(rows[:, 51].astype(np.int64), topo["bFaces"])
+    assert np.array_equal(rows[:, 52], gold["sigma_by_tag"][topo["tags"][t] - 1])
+    assert not os.path.exists(tmp + "/boundaries.dat")  # MT has natural boundary conditions only
+
+
+@pytest.mark.gpu
+def test_kernel_cli_mt_two_polarizations(tmp_path, topo):
+    """kernel.py in MT mode (p=1): both polarizations assembled from the 1-D excitation, solved in
+    lockstep, and each x{i}.dat solves its system: ||b_i - A x_i|| <= 1e-7 ||b_i|| with A, b from the
+    oracle-checked pieces (fused assembly without Dirichlet rows, mt_rhs)."""
+    import torch
+
+    from petgem_b200.parallel import readPetscMatrix, readPetscVector
+
+    params, opts = make_mt_case(tmp_path, topo, nord=1)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params],
+                         capture_output=True, text=True, timeout=1200)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    from petgem_b200 import mt
+    from petgem_b200.device import AssemblyPlan, CSRMatrix, ElementData
+
+    tmp = str(tmp_path / "tmp")
+    rows = readPetscMatrix(tmp + "/boundaryElements.dat").array.real
+    omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
+    elem_z = topo["nodes"][topo["elemsN"]][:, :, 2]
+    N = int(topo["total_dofs_p1"])
+    bs = mt.mt_rhs(rows, elem_z.max(), elem_z.min(), 1, omega, mu, ["x", "y"], N)
+    sig = np.array([1.0, 0.01, 1.0, 3.3333])[topo["tags"] - 1]
+    el = ElementData.from_mesh(topo["nodes"], topo["elemsN"], topo["elemsE"], topo["edgesNodes"], topo["elemsF"],
+                               topo["facesE"], np.stack([sig, sig], axis=1))
+    plan = AssemblyPlan(el, 1, order="reference")
+    geo, code = el.geometry()
+    A = CSRMatrix(*plan.csr(), plan.assemble(geo, code, omega, mu), plan.N)
+    for i in range(2):
+        x = readPetscVector(tmp + "/x%d.dat" % i).getArray()
+        b = torch.as_tensor(bs[i], device=A.vals.device)
+        r = b - A.mult(torch.as_tensor(x, device=A.vals.device))
+        assert float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(b)) <= 1e-7
+    assert os.path.exists(str(tmp_path / "out" / "fields.npz"))
