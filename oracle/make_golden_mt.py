@@ -11,7 +11,8 @@ write for tests/data/test_mesh.msh (mesh.computeBoundaryFaces / computeFacePlane
 computeBoundaryElements).  The 1-D problem uses N1D nodes instead of the hard-wired 1e6
 (solver.py:403) to keep the reference's Python loops short; the product takes the same parameter.
 
-    python oracle/make_golden_mt.py   ->  tests/golden/mt_rhs.npz
+    python oracle/make_golden_mt.py           ->  tests/golden/mt_rhs.npz
+    python oracle/make_golden_mt.py --rules   ->  tests/golden/triangle_rules.npz
 """
 import os
 import sys
@@ -145,5 +146,20 @@ def main():
     print("wrote", os.path.join(GOLD, "mt_rhs.npz"))
 
 
+def rules():
+    """The reference's 2-D rules of order 2p, p = 1..6 (hvfem.compute2DGaussPoints) ->
+    tests/golden/triangle_rules.npz"""
+    hvfem, _, _ = refshim.load()
+    out = {}
+    for deg in (2, 4, 6, 8, 10, 12):
+        pts, w = hvfem.compute2DGaussPoints(deg)
+        out["pts_%d" % deg], out["w_%d" % deg] = np.asarray(pts, dtype=np.float64), np.asarray(w, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "triangle_rules.npz"), **out)
+    print("wrote", os.path.join(GOLD, "triangle_rules.npz"))
+
+
 if __name__ == "__main__":
-    main()
+    if "--rules" in sys.argv:
+        rules()
+    else:
+        main()

@@ -8,7 +8,9 @@ For each degree d the orbit structure below (the classical minimal-point structu
 D. A. Dunavant, Int. J. Numer. Meth. Eng. 21 (1985) 1129-1148) is solved for exactness on every
 monomial x^i y^j, i + j <= d, over the unit triangle (integral i! j! / (i+j+2)!) by
 Gauss-Newton from random starts, keeping the solution with positive weights and interior points.
-Prints the orbit parameters with 17 significant digits.
+Prints the orbit parameters with 17 significant digits.  Degrees 2..8 converge in seconds; for the
+25- and 33-point rules (degrees 10, 12) random starts have not converged within minutes, so
+petgem_b200/quadrature2d.py falls back to a product rule there.
 """
 import math
 import sys
@@ -39,22 +41,29 @@ def expand(params, struct):
     return np.array(pts), np.array(wts)
 
 
-def residual(params, struct, degree):
+def _moments(degree):
+    ij = [(i, j) for i in range(degree + 1) for j in range(degree + 1 - i)]
+    ex = np.array([math.factorial(i) * math.factorial(j) / math.factorial(i + j + 2) for i, j in ij])
+    return np.array([i for i, _ in ij]), np.array([j for _, j in ij]), ex
+
+
+def residual(params, struct, degree, mom=None):
+    I, J, ex = mom or _moments(degree)
     pts, wts = expand(params, struct)
     x, y = pts[:, 0], pts[:, 1]
-    res = []
-    for i in range(degree + 1):
-        for j in range(degree + 1 - i):
-            exact = math.factorial(i) * math.factorial(j) / math.factorial(i + j + 2)
-            res.append((wts * x**i * y**j).sum() - exact)
-    return np.array(res)
+    return (wts[None, :] * x[None, :] ** I[:, None] * y[None, :] ** J[:, None]).sum(axis=1) - ex
 
 
-def solve(degree, seed=0, tries=400):
+def solve(degree, seed=0, tries=4000, want=8):
+    """Gauss-Newton (Levenberg-Marquardt) from random starts until `want` admissible solutions (positive
+    weights, interior points; usually several copies of one or two distinct rules) have been found or the
+    tries are used up."""
     struct = STRUCTURE[degree]
     n3, n21, n111 = struct
+    mom = _moments(degree)
     rng = np.random.default_rng(seed)
-    best = None
+    best = {}
+    found = 0
     for _ in range(tries):
         p0 = []
         for _ in range(n3):
@@ -62,15 +71,22 @@ def solve(degree, seed=0, tries=400):
         for _ in range(n21):
             p0 += [rng.uniform(0.005, 0.08), rng.uniform(0.02, 0.49)]
         for _ in range(n111):
-            a = rng.uniform(0.01, 0.4); b = rng.uniform(0.05, 0.9 - a)
+            a = rng.uniform(0.01, 0.4)
+            b = rng.uniform(0.05, 0.9 - a)
             p0 += [rng.uniform(0.005, 0.05), a, b]
-        sol = least_squares(residual, p0, args=(struct, degree), xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=2000)
+        sol = least_squares(residual, p0, args=(struct, degree, mom), method="lm", xtol=1e-15, ftol=1e-15,
+                            gtol=1e-15, max_nfev=400)
+        if np.abs(sol.fun).max() > 1e-10:
+            continue
+        sol = least_squares(residual, sol.x, args=(struct, degree, mom), method="lm", xtol=3e-16, ftol=3e-16,
+                            gtol=3e-16, max_nfev=400)
         pts, wts = expand(sol.x, struct)
         if np.abs(sol.fun).max() < 5e-16 and (wts > 0).all() and (pts > 0).all():
-            key = tuple(np.round(np.sort(wts), 10))
-            if best is None:
-                best = {}
+            key = tuple(np.round(np.sort(wts), 9))
             best.setdefault(key, sol.x)
+            found += 1
+            if found >= want:
+                break
     return struct, best
 
 
