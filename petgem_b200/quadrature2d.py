@@ -1,4 +1,4 @@
-"""Quadrature rules on the unit triangle, degrees 2..12 (even); fully symmetric up to degree 8.
+"""Quadrature rules on the unit triangle, degrees 2..12 (even); fully symmetric up to degree 10.
 
 The reference tabulates "order 2p" rules for the MT boundary integrals
 (``hvfem.compute2DGaussPoints``, hvfem.py:1613-2300, called at solver.py:323-324): the classical
@@ -9,7 +9,7 @@ for agreement with the reference.  The orbit parameters below were re-derived, n
 ``tools/make_triangle_rules.py`` solves the moment equations for the published orbit structures
 (S3 = centroid, S21(a) = permutations of (a, a, 1-2a), S111(a, b) = permutations of (a, b, 1-a-b));
 ``tests/test_mt.py`` checks exactness on every monomial up to the degree and the agreement with the
-reference's points (as a set) to 1e-12 (the reference prints ~15 digits) for degrees 2..8.
+reference's points (as a set) to 1e-12 (the reference prints ~15 digits) for degrees 2..10.
 
 Weights sum to 1/2 (the area of the unit triangle), as in the reference.
 """
@@ -30,6 +30,12 @@ _ORBITS = {
         ("s21", 0.016229248811595157, 0.050547228317029569),
         ("s21", 0.051608685267356312, 0.17056930775183615),
         ("s111", 0.013615157087229119, 0.2631128296344189, 0.0083947774100495039)],
+    10: [("s3", 0.045408995191662985),
+         ("s21", 0.018362978878201666, 0.48557763338372001),
+         ("s21", 0.022660529717727262, 0.10948157548484638),
+         ("s111", 0.014163621265468333, 0.24667256063955986, 0.72832390459791163),
+         ("s111", 0.03637895842277928, 0.55035294182147942, 0.14170721941450812),
+         ("s111", 0.0047108334818440926, 0.0095408154002988143, 0.92365593358769249)],
 }
 
 
@@ -47,12 +53,11 @@ def _conical_rule(degree: int):
 
 def triangle_quadrature(degree: int):
     """Points (xi, eta) [ng, 2] and weights [ng] of a rule exact for polynomials of the given (even)
-    degree on the triangle (0,0), (1,0), (0,1): the symmetric rule the reference uses for degrees 2..8
-    (p <= 4); for degrees 10 and 12 (p = 5, 6) a collapsed Gauss-Jacobi product rule of the same
-    exactness -- the 25- and 33-point symmetric rules have not been re-derived yet, so at p >= 5 the MT
-    right-hand side agrees with the reference up to the quadrature error of its non-polynomial integrand
-    only."""
-    if degree in (10, 12):
+    degree on the triangle (0,0), (1,0), (0,1): the symmetric rule the reference uses for degrees 2..10
+    (p <= 5); for degree 12 (p = 6) a collapsed Gauss-Jacobi product rule of the same exactness -- the
+    33-point symmetric rule has not been re-derived yet, so at p = 6 the MT right-hand side agrees with
+    the reference up to the quadrature error of its non-polynomial integrand only."""
+    if degree == 12:
         return _conical_rule(degree)
     if degree not in _ORBITS:
         raise ValueError("triangle_quadrature: degree %r not tabulated (%s)" % (degree, sorted(_ORBITS)))

@@ -18,7 +18,7 @@ def test_triangle_rules_are_exact(degree):
     from petgem_b200.quadrature2d import triangle_quadrature
 
     pts, w = triangle_quadrature(degree)
-    assert pts.shape[0] == {2: 3, 4: 6, 6: 12, 8: 16, 10: 36, 12: 49}[degree]  # 10, 12: product rules
+    assert pts.shape[0] == {2: 3, 4: 6, 6: 12, 8: 16, 10: 25, 12: 49}[degree]  # 12: product rule
     assert (w > 0).all() and (pts > 0).all() and (pts.sum(axis=1) < 1).all()
     for i in range(degree + 1):
         for j in range(degree + 1 - i):
@@ -26,7 +26,7 @@ def test_triangle_rules_are_exact(degree):
             assert abs((w * pts[:, 0] ** i * pts[:, 1] ** j).sum() - exact) <= 2e-16 + 1e-14 * exact
 
 
-@pytest.mark.parametrize("degree", [2, 4, 6, 8])
+@pytest.mark.parametrize("degree", [2, 4, 6, 8, 10])
 def test_triangle_rules_are_the_reference_rules(degree):
     """Same point set and weights as hvfem.compute2DGaussPoints(degree) (order of the points aside)."""
     from petgem_b200.quadrature2d import triangle_quadrature
@@ -78,7 +78,7 @@ def _boundary_rows(topo, gold, p):
     return rows, total
 
 
-@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("p", [1, 2, 3])
 def test_mt_rhs_matches_reference(gold, topo, p):
     """b for both polarizations on the reference's test mesh == the reference's boundary loop
     (solver.py:318-512 driven with the reference's own functions, oracle/make_golden_mt.py)."""
@@ -98,6 +98,8 @@ def test_mt_rhs_matches_reference(gold, topo, p):
         # The reference as shipped loses the Gauss points of top faces whose z rounds above z_max (u = 0
         # instead of 1, a rounding artefact of mt1d.linearInterp1D); the vectors above were recorded with
         # those points clipped to z_max.  The raw outcome differs from them on dofs of the top faces only.
+        if p > 2:
+            continue  # recorded at p = 1, 2 only
         raw = np.zeros(total, dtype=np.complex128)
         raw[gold["b_%s_p%d_raw_idx" % (pol, p)]] = gold["b_%s_p%d_raw_val" % (pol, p)]
         differs = np.nonzero(np.abs(raw - ref) > 1e-12 * np.abs(ref).max())[0]

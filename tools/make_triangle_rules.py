@@ -8,9 +8,10 @@ For each degree d the orbit structure below (the classical minimal-point structu
 D. A. Dunavant, Int. J. Numer. Meth. Eng. 21 (1985) 1129-1148) is solved for exactness on every
 monomial x^i y^j, i + j <= d, over the unit triangle (integral i! j! / (i+j+2)!) by
 Gauss-Newton from random starts, keeping the solution with positive weights and interior points.
-Prints the orbit parameters with 17 significant digits.  Degrees 2..8 converge in seconds; for the
-25- and 33-point rules (degrees 10, 12) random starts have not converged within minutes, so
-petgem_b200/quadrature2d.py falls back to a product rule there.
+Prints the orbit parameters with 17 significant digits.  Degrees 2..8 converge in seconds; the
+25-point rule (degree 10) needed an analytic Jacobian and ~10 minutes of random starts; for the
+33-point rule (degree 12) none has converged yet, so petgem_b200/quadrature2d.py falls back to a
+product rule there.
 """
 import math
 import sys
@@ -54,10 +55,55 @@ def residual(params, struct, degree, mom=None):
     return (wts[None, :] * x[None, :] ** I[:, None] * y[None, :] ** J[:, None]).sum(axis=1) - ex
 
 
-def solve(degree, seed=0, tries=4000, want=8):
-    """Gauss-Newton (Levenberg-Marquardt) from random starts until `want` admissible solutions (positive
-    weights, interior points; usually several copies of one or two distinct rules) have been found or the
-    tries are used up."""
+def jacobian(params, struct, degree, mom=None):
+    """Analytic Jacobian of `residual` with respect to the orbit parameters."""
+    I, J, _ = mom or _moments(degree)
+    n3, n21, n111 = struct
+
+    def mono(x, y):
+        return x**I * y**J
+
+    def dmono(x, y):
+        dx = np.where(I > 0, I * x ** np.maximum(I - 1, 0) * y**J, 0.0)
+        dy = np.where(J > 0, J * x**I * y ** np.maximum(J - 1, 0), 0.0)
+        return dx, dy
+
+    cols, k = [], 0
+    for _ in range(n3):
+        cols.append(mono(1 / 3, 1 / 3))
+        k += 1
+    for _ in range(n21):
+        w, a = params[k], params[k + 1]
+        k += 2
+        c = 1 - 2 * a
+        orbit = [(a, a, (1, 1)), (a, c, (1, -2)), (c, a, (-2, 1))]  # (x, y, d(x, y)/da)
+        cols.append(sum(mono(x, y) for x, y, _ in orbit))
+        d = 0
+        for x, y, (sx, sy) in orbit:
+            dx, dy = dmono(x, y)
+            d = d + w * (dx * sx + dy * sy)
+        cols.append(d)
+    for _ in range(n111):
+        w, a, b = params[k], params[k + 1], params[k + 2]
+        k += 3
+        c = 1 - a - b
+        orbit = [(a, b, (1, 0), (0, 1)), (a, c, (1, -1), (0, -1)), (b, a, (0, 1), (1, 0)),
+                 (b, c, (0, -1), (1, -1)), (c, a, (-1, 1), (-1, 0)), (c, b, (-1, 0), (-1, 1))]
+        cols.append(sum(mono(x, y) for x, y, _, _ in orbit))
+        da = db = 0
+        for x, y, (xa, ya), (xb, yb) in orbit:
+            dx, dy = dmono(x, y)
+            da = da + w * (dx * xa + dy * ya)
+            db = db + w * (dx * xb + dy * yb)
+        cols.append(da)
+        cols.append(db)
+    return np.stack(cols, axis=1)
+
+
+def solve(degree, seed=0, tries=4000, want=4):
+    """Levenberg-Marquardt from random starts until `want` admissible solutions (positive weights,
+    interior points; usually copies of one or two distinct rules) have been found or the tries are
+    used up."""
     struct = STRUCTURE[degree]
     n3, n21, n111 = struct
     mom = _moments(degree)
@@ -74,12 +120,8 @@ def solve(degree, seed=0, tries=4000, want=8):
             a = rng.uniform(0.01, 0.4)
             b = rng.uniform(0.05, 0.9 - a)
             p0 += [rng.uniform(0.005, 0.05), a, b]
-        sol = least_squares(residual, p0, args=(struct, degree, mom), method="lm", xtol=1e-15, ftol=1e-15,
-                            gtol=1e-15, max_nfev=400)
-        if np.abs(sol.fun).max() > 1e-10:
-            continue
-        sol = least_squares(residual, sol.x, args=(struct, degree, mom), method="lm", xtol=3e-16, ftol=3e-16,
-                            gtol=3e-16, max_nfev=400)
+        sol = least_squares(residual, p0, jac=jacobian, args=(struct, degree, mom), method="lm", xtol=1e-15,
+                            ftol=1e-15, gtol=1e-15, max_nfev=2000)
         pts, wts = expand(sol.x, struct)
         if np.abs(sol.fun).max() < 5e-16 and (wts > 0).all() and (pts > 0).all():
             key = tuple(np.round(np.sort(wts), 9))
