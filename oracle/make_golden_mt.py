@@ -13,6 +13,7 @@ computeBoundaryElements).  The 1-D problem uses N1D nodes instead of the hard-wi
 
     python oracle/make_golden_mt.py           ->  tests/golden/mt_rhs.npz
     python oracle/make_golden_mt.py --rules   ->  tests/golden/triangle_rules.npz
+    python oracle/make_golden_mt.py --impedance -> tests/golden/mt_impedance.npz
 """
 import os
 import sys
@@ -148,6 +149,27 @@ def main():
     print("wrote", os.path.join(GOLD, "mt_rhs.npz"))
 
 
+def impedance():
+    """computeImpedance of the reference's postprocessing.py on random fields.  The module itself cannot be
+    imported (h5py, meshio, petsc4py): the one pure-numpy function is compiled from its source text."""
+    import ast
+
+    refshim.load()
+    path = os.path.join(refshim.REFERENCE_ROOT, "petgem", "postprocessing.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "computeImpedance"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(11)
+    fields = [rng.normal(size=(9, 6)) + 1j * rng.normal(size=(9, 6)) for _ in range(2)]
+    omega, mu = 2 * np.pi * FREQ, 4e-7 * np.pi
+    res, phase, tipper, imp = ns["computeImpedance"](fields, omega, mu)
+    np.savez_compressed(os.path.join(GOLD, "mt_impedance.npz"), f0=fields[0], f1=fields[1], omega=omega, mu=mu,
+                        apparent_resistivity=np.stack(res), phase=np.stack(phase), tipper=np.stack(tipper),
+                        impedance=np.stack(imp))
+    print("wrote", os.path.join(GOLD, "mt_impedance.npz"))
+
+
 def rules():
     """The reference's 2-D rules of order 2p, p = 1..6 (hvfem.compute2DGaussPoints) ->
     tests/golden/triangle_rules.npz"""
@@ -163,5 +185,7 @@ def rules():
 if __name__ == "__main__":
     if "--rules" in sys.argv:
         rules()
+    elif "--impedance" in sys.argv:
+        impedance()
     else:
         main()

@@ -48,6 +48,23 @@ def fieldInterpolator(solution_vector, nodes, elemsN, elemsE, edgesN, elemsF, fa
     return fields
 
 
+def computeImpedance(fields, omega, mu):
+    """postprocessing.py:619-688 -> (apparent resistivity [4], phase [4], tipper [2], impedance [4]), each
+    entry an array over the receivers, components ordered xx, xy, yx, yy (tipper: x, y).  The impedance
+    tensor solves E = Z H for the two polarizations, the tipper Hz = T (Hx, Hy): 2x2 systems per receiver."""
+    f1, f2 = np.asarray(fields[0]), np.asarray(fields[1])
+    E = np.stack([np.stack([f1[:, 0], f2[:, 0]], axis=-1), np.stack([f1[:, 1], f2[:, 1]], axis=-1)], axis=-2)
+    H = np.stack([np.stack([f1[:, 3], f2[:, 3]], axis=-1), np.stack([f1[:, 4], f2[:, 4]], axis=-1)], axis=-2)
+    Hz = np.stack([f1[:, 5], f2[:, 5]], axis=-1)[:, None, :]
+    Hinv = np.linalg.inv(H)
+    Z = E @ Hinv
+    T = (Hz @ Hinv)[:, 0, :]
+    impedance = [Z[:, 0, 0], Z[:, 0, 1], Z[:, 1, 0], Z[:, 1, 1]]
+    apparent_resistivity = [np.abs(z) ** 2 / (mu * omega) for z in impedance]
+    phase = [(np.degrees(np.arctan(-np.imag(z) / np.real(z)))) % 360 for z in impedance]
+    return apparent_resistivity, phase, [T[:, 0], T[:, 1]], impedance
+
+
 class Postprocessing():
     """Class for postprocessing."""
 
@@ -65,6 +82,12 @@ class Postprocessing():
                 x = readPetscVector(out_dir + '/x%d.dat' % i)
                 out['fields_%d' % i] = fieldInterpolator(x, tab['nodes'], tab['elemsN'], tab['elemsE'], tab['edgesNodes'],
                                                          tab['elemsF'], tab['facesE'], tab['dofs'], receivers, inputSetup)
+            if inputSetup.model.get('mode') == 'mt' and inputSetup.run.get('num_polarizations') == 2:
+                freq = inputSetup.model.get('mt').get('frequency')
+                res, phase, tipper, imp = computeImpedance([out['fields_0'], out['fields_1']],
+                                                           2. * np.pi * freq, 4. * np.pi * 1e-7)
+                out.update(apparent_resistivity=np.stack(res), phase=np.stack(phase), tipper=np.stack(tipper),
+                           impedance=np.stack(imp))
             out['receiver_coordinates'] = receivers
             out['run_time_s'] = Timers().elapsed('Assembly') + Timers().elapsed('Solver')
             np.savez(inputSetup.output.get('directory') + '/fields.npz', **out)

@@ -105,3 +105,16 @@ def test_mt_rhs_matches_reference(gold, topo, p):
         differs = np.nonzero(np.abs(raw - ref) > 1e-12 * np.abs(ref).max())[0]
         assert np.isin(differs, top_dofs).all()
         assert (differs.size > 0) == (int(gold["artefact_points_p%d" % p]) > 0 and pol in ("x", "y"))
+
+
+def test_impedance_matches_reference():
+    """MT post-processing formula (postprocessing.py:619-688) on recorded random fields."""
+    from petgem_b200.postprocessing import computeImpedance
+
+    g = golden("mt_impedance.npz")
+    res, phase, tipper, imp = computeImpedance([g["f0"], g["f1"]], float(g["omega"]), float(g["mu"]))
+    for mine, key in ((imp, "impedance"), (res, "apparent_resistivity"), (tipper, "tipper")):
+        ref = g[key]
+        assert np.abs(np.stack(mine) - ref).max() <= 1e-11 * np.abs(ref).max(), key
+    dphi = np.abs(np.stack(phase) - g["phase"])
+    assert np.minimum(dphi, 360.0 - dphi).max() <= 1e-8
