@@ -118,3 +118,36 @@ def test_impedance_matches_reference():
         assert np.abs(np.stack(mine) - ref).max() <= 1e-11 * np.abs(ref).max(), key
     dphi = np.abs(np.stack(phase) - g["phase"])
     assert np.minimum(dphi, 360.0 - dphi).max() <= 1e-8
+
+
+def test_interpolation_rule_edge_cases():
+    """The sweep of mt1d.linearInterp1D (mt1d.py:96-127), restated literally as the checker: inside the
+    nodes linear, below the first node extrapolated with the first segment, above the last node zero."""
+    from petgem_b200.mt import _interp_first_segments
+
+    def sweep(x, u, xp):
+        xps_pos, xs_pos = np.argsort(xp), np.argsort(x)
+        xps, xs, us = xp[xps_pos], x[xs_pos], u[xs_pos]
+        ups = np.zeros_like(xp, dtype=u.dtype)
+        ini = 0
+        for i in range(1, x.size):
+            for j in range(ini, xp.size):
+                if xps[j] > xs[i]:
+                    ini = j
+                    break
+                h = xs[i] - xs[i - 1]
+                xi = (2 * xps[j] - xs[i] - xs[i - 1]) / h
+                ups[j] = 0.5 * (1 - xi) * us[i - 1] + 0.5 * (1 + xi) * us[i]
+                ini = j + 1
+        out = np.zeros_like(ups)
+        out[xps_pos] = ups
+        return out
+
+    rng = np.random.default_rng(2)
+    for n in (2, 3, 17):
+        x = np.sort(rng.uniform(-10.0, 10.0, size=n))
+        u = rng.normal(size=n) + 1j * rng.normal(size=n)
+        xp = np.concatenate([rng.uniform(-15.0, 15.0, size=40), x, [x[0] - 1.0, x[-1] + 1e-9, x[-1]]])
+        got, ref = _interp_first_segments(x, u, xp), sweep(x, u, xp)
+        assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1.0)
+        assert got[-2] == 0 and got[-1] == u[-1]  # just above the last node: zero; on it: the nodal value
