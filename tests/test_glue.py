@@ -260,15 +260,16 @@ def test_mt_preprocessing_writes_boundary_elements(tmp_path, topo):
 
 
 @pytest.mark.gpu
-def test_kernel_cli_mt_two_polarizations(tmp_path, topo):
-    """kernel.py in MT mode (p=1): both polarizations assembled from the 1-D excitation, solved in
+@pytest.mark.parametrize("nord", [1, 2])
+def test_kernel_cli_mt_two_polarizations(tmp_path, topo, nord):
+    """kernel.py in MT mode (p=1, 2): both polarizations assembled from the 1-D excitation, solved in
     lockstep, and each x{i}.dat solves its system: ||b_i - A x_i|| <= 1e-7 ||b_i|| with A, b from the
     oracle-checked pieces (fused assembly without Dirichlet rows, mt_rhs)."""
     import torch
 
     from petgem_b200.parallel import readPetscMatrix, readPetscVector
 
-    params, opts = make_mt_case(tmp_path, topo, nord=1)
+    params, opts = make_mt_case(tmp_path, topo, nord=nord)
     res = subprocess.run([sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params],
                          capture_output=True, text=True, timeout=1200)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
@@ -279,12 +280,12 @@ def test_kernel_cli_mt_two_polarizations(tmp_path, topo):
     rows = readPetscMatrix(tmp + "/boundaryElements.dat").array.real
     omega, mu = 2 * np.pi * 2.0, 4e-7 * np.pi
     elem_z = topo["nodes"][topo["elemsN"]][:, :, 2]
-    N = int(topo["total_dofs_p1"])
-    bs = mt.mt_rhs(rows, elem_z.max(), elem_z.min(), 1, omega, mu, ["x", "y"], N)
+    N = int(topo["total_dofs_p%d" % nord])
+    bs = mt.mt_rhs(rows, elem_z.max(), elem_z.min(), nord, omega, mu, ["x", "y"], N)
     sig = np.array([1.0, 0.01, 1.0, 3.3333])[topo["tags"] - 1]
     el = ElementData.from_mesh(topo["nodes"], topo["elemsN"], topo["elemsE"], topo["edgesNodes"], topo["elemsF"],
                                topo["facesE"], np.stack([sig, sig], axis=1))
-    plan = AssemblyPlan(el, 1, order="reference")
+    plan = AssemblyPlan(el, nord, order="reference")
     geo, code = el.geometry()
     A = CSRMatrix(*plan.csr(), plan.assemble(geo, code, omega, mu), plan.N)
     for i in range(2):
