@@ -8,10 +8,11 @@ For each degree d the orbit structure below (the classical minimal-point structu
 D. A. Dunavant, Int. J. Numer. Meth. Eng. 21 (1985) 1129-1148) is solved for exactness on every
 monomial x^i y^j, i + j <= d, over the unit triangle (integral i! j! / (i+j+2)!) by
 Gauss-Newton from random starts, keeping the solution with positive weights and interior points.
-Prints the orbit parameters with 17 significant digits.  Degrees 2..8 converge in seconds; the
-25-point rule (degree 10) needed an analytic Jacobian and ~10 minutes of random starts; for the
-33-point rule (degree 12) none has converged yet, so petgem_b200/quadrature2d.py falls back to a
-product rule there.
+Prints the orbit parameters with 17 significant digits.  Degrees 2..8 converge in seconds and the
+25-point rule (degree 10) in ~10 minutes of random starts; for the 33-point rule (degree 12) random
+starts did not converge; re-solving it from the published 15-digit values (`START`) takes the moment
+residual from 2e-15 to 3e-17 but moves the points by 1e-10 (ill conditioned), so quadrature2d.py keeps the
+published digits for that rule.
 """
 import math
 import sys
@@ -21,6 +22,17 @@ from scipy.optimize import least_squares
 
 STRUCTURE = {  # degree: (number of S3, S21, S111 orbits)
     2: (0, 1, 0), 4: (0, 2, 0), 6: (0, 2, 1), 8: (1, 3, 1), 10: (1, 2, 3), 12: (0, 5, 3),
+}
+
+
+# published 33-point rule (weights for the unit-area normalisation halved), starting guess only
+START = {
+    12: [0.025731066440455 / 2, 0.488217389773805, 0.043692544538038 / 2, 0.439724392294460,
+         0.062858224217885 / 2, 0.271210385012116, 0.034796112930709 / 2, 0.127576145541586,
+         0.006166261051559 / 2, 0.021317350453210,
+         0.040371557766381 / 2, 0.115343494534698, 0.275713269685514,
+         0.022356773202303 / 2, 0.022838332222257, 0.281325580989940,
+         0.017316231108659 / 2, 0.025734050548330, 0.116251915907597],
 }
 
 
@@ -110,6 +122,10 @@ def solve(degree, seed=0, tries=4000, want=4):
     rng = np.random.default_rng(seed)
     best = {}
     found = 0
+    if degree in START:
+        sol = least_squares(residual, START[degree], jac=jacobian, args=(struct, degree, mom), method="lm",
+                            xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=2000)
+        return struct, {"from the published starting guess": sol.x}
     for _ in range(tries):
         p0 = []
         for _ in range(n3):
