@@ -168,7 +168,7 @@ def mt_rhs(boundary_rows, z_max, z_min, Nord, omega, mu, polarizations, total_do
     const = 1j * omega * mu
     modes = [{"x": 1, "y": 2}.get(pol, pol) for pol in polarizations]
     out = [np.zeros(int(total_dofs), dtype=np.complex128) for _ in modes]
-    chunk = 4096  # boundary faces per pass: bounds the [faces, n, ng, 3] temporaries
+    chunk = max(64, (1 << 23) // (n * ng * 3))  # boundary faces per pass: [faces, n, ng, 3] temporaries <= 64 MB
     for c0 in range(0, nb, chunk):
         sl = slice(c0, min(c0 + chunk, nb))
         Nref = Nexp[face_local[sl, None], Jx[sl]] * S[sl, :, None, None]              # [nc, n, ng, 3]
