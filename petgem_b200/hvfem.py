@@ -74,6 +74,29 @@ def computeElementOrientation(edgesEle, nodesEle, edgesNodesEle, globalEdgesInFa
     return eo, fo
 
 
+def computeElementOrientation_batch(edgesEle, nodesEle, edgesNodesEle, globalEdgesInFace):
+    """computeElementOrientation for many elements at once (host numpy): edgesEle [m,6], nodesEle [m,4],
+    edgesNodesEle [m,6,2], globalEdgesInFace [m,4,3] -> (edge_orientation [m,6], face_orientation [m,4])."""
+    edgesEle, nodesEle = np.asarray(edgesEle), np.asarray(nodesEle)
+    edgesNodesEle, gef = np.asarray(edgesNodesEle), np.asarray(globalEdgesInFace)
+    a = np.array([e[0] for e in _EDGE_LOCAL])
+    b = np.array([e[1] for e in _EDGE_LOCAL])
+    eo = ((nodesEle[:, a] == edgesNodesEle[:, :, 1]) & (nodesEle[:, b] == edgesNodesEle[:, :, 0])).astype(np.int64)
+    lut = np.zeros(34, dtype=np.int64)
+    for code, val in _FACE_CODE.items():
+        lut[code] = val
+    fo = np.zeros((edgesEle.shape[0], 4), dtype=np.int64)
+    for i, le in enumerate(_FACE_LOCAL_EDGES):
+        # position (1-based, 0 = absent; the last match wins like the reference's loop) of the face's first
+        # two local edges in the global face's edge triple
+        m1 = edgesEle[:, le[0], None] == gef[:, i, :]
+        m2 = edgesEle[:, le[1], None] == gef[:, i, :]
+        k1 = np.where(m1.any(axis=1), 3 - np.argmax(m1[:, ::-1], axis=1), 0)
+        k2 = np.where(m2.any(axis=1), 3 - np.argmax(m2[:, ::-1], axis=1), 0)
+        fo[:, i] = lut[10 * k1 + k2]
+    return eo, fo
+
+
 def pack_orientation(edge_orientation, face_orientation):
     """(eo [...,6], fo [...,4]) -> uint32 code used by the kernels (include/petgem_b200.h)."""
     eo = np.asarray(edge_orientation, dtype=np.uint32)

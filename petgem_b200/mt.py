@@ -158,10 +158,7 @@ def mt_rhs(boundary_rows, z_max, z_min, Nord, omega, mu, polarizations, total_do
     v1 = np.take_along_axis(coord, fnodes[:, 1][:, None, None].repeat(3, axis=2), axis=1)[:, 0]
     v2 = np.take_along_axis(coord, fnodes[:, 2][:, None, None].repeat(3, axis=2), axis=1)[:, 0]
     det2d = np.linalg.norm(np.cross(v1 - v0, v2 - v0), axis=1)
-    eo = np.zeros((nb, 6), dtype=np.int64)
-    fo = np.zeros((nb, 4), dtype=np.int64)
-    for e in range(nb):
-        eo[e], fo[e] = hvfem.computeElementOrientation(edges_ele[e], nodes_ele[e], edges_nodes[e], edges_face[e])
+    eo, fo = hvfem.computeElementOrientation_batch(edges_ele, nodes_ele, edges_nodes, edges_face)
     Jx, S = basis.local_to_expanded(p, eo, fo)  # [nb, n]
     # expanded functions at the quadrature points of the four local faces
     Nexp = np.stack([basis.evaluate_expanded(p, ref_pts[f])[0] for f in range(4)])  # [4, nexp, ng, 3]

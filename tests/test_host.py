@@ -171,3 +171,13 @@ def test_reference_tensors_are_small_integers(p):
     assert max(np.abs(nM).max(), np.abs(nK).max()) < (32768 if p <= 3 else 2 ** 31)
     if p == 2:
         assert np.abs(nM).max() == 252 and np.abs(nK).max() == 160
+
+
+def test_batched_orientation_equals_reference_table(topo):
+    """hvfem.computeElementOrientation_batch on the whole test mesh == the reference's per-element codes."""
+    from petgem_b200 import hvfem
+
+    eo, fo = hvfem.computeElementOrientation_batch(topo["elemsE"], topo["elemsN"], topo["edgesNodes"][topo["elemsE"]],
+                                                   topo["facesE"][topo["elemsF"]])
+    assert np.array_equal(eo, topo["orient"][:, :6]) and np.array_equal(fo, topo["orient"][:, 6:])
+    assert len(set(map(int, fo.reshape(-1)))) == 6  # all six face codes occur on this mesh
