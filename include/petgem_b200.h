@@ -265,6 +265,16 @@ int pg_zbdiv(int k, const double *a, const double *b, double *out, void *stream)
 int pg_cocg_step(int64_t n, int k, const double *alpha2, const double *P, const double *Q, const double *dinv,
                  double *X, double *R, double *Z, double *out, void *work, void *stream);
 
+/* The whole solve as one call on one GPU (full matrix): COCG (method 0, -ksp_type cg -ksp_cg_type
+ * symmetric) or COCR (method 1, -ksp_type cr) with optional Jacobi preconditioning, zero initial guess,
+ * convergence on ||M^-1 r|| <= rtol ||M^-1 b|| checked every check_every iterations (solver.py:584-590).
+ * work = pg_krylov_workspace_bytes(n) bytes of device memory; iterations and rel_residual are host
+ * outputs; returns PG_OK also when maxit is reached (compare rel_residual with rtol). */
+int64_t pg_krylov_workspace_bytes(int64_t n);
+int pg_krylov_solve(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *b,
+                    double *x, int method, int jacobi, double rtol, int maxit, int check_every, void *work,
+                    int *iterations, double *rel_residual, void *stream);
+
 /* CUDA graph of a batch of the calls above (the launches of the Krylov iterations between two host
  * checks of the residual): begin capture on a NON-default stream, issue the calls, end -> executable
  * graph, launch it any number of times. */

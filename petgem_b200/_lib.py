@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -112,6 +112,9 @@ SIGNATURES = {
     "pg_cocr_direction": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
     "pg_zbnrm2sq": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbdiv": (C.c_int, [_i32, _p, _p, _p, _p]),
+    "pg_krylov_workspace_bytes": (_i64, [_i64]),
+    "pg_krylov_solve": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i32, _i32, _d, _i32, _i32, _p, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_double), _p]),
     "pg_graph_begin": (C.c_int, [_p]),
     "pg_graph_end": (C.c_int, [_p, C.POINTER(_p)]),
     "pg_graph_launch": (C.c_int, [_p, _p]),

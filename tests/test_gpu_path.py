@@ -478,6 +478,20 @@ def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
         r8 = krylov.solve(A, bd, {"ksp_type": ksp, "ksp_cg_type": "symmetric", "pc_type": "jacobi", "ksp_rtol": 1e-8,
                                   "ksp_max_it": 20000})
         assert r8.converged and -10 <= r8.iterations - its_ref <= 10 + its_ref // 50, (ksp, r8.iterations, its_ref)
+        # the same solve as ONE C-ABI call (pg_krylov_solve): same iteration count, same solution
+        import ctypes as C
+
+        from petgem_b200._lib import check, lib, ptr, stream_ptr
+        L = lib()
+        n = A.rows
+        work = torch.empty((L.pg_krylov_workspace_bytes(n) // 16,), dtype=torch.complex128, device=bd.device)
+        xc = torch.empty_like(bd)
+        its, rel = C.c_int(0), C.c_double(0.0)
+        check(L.pg_krylov_solve(n, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), ptr(bd), ptr(xc), 0 if ksp == "cg" else 1,
+                                1, 1e-8, 20000, 10, ptr(work), C.byref(its), C.byref(rel), stream_ptr()),
+              "pg_krylov_solve")
+        assert rel.value <= 1e-8 and abs(its.value - r8.iterations) <= 10, (ksp, its.value, r8.iterations, rel.value)
+        assert float(torch.linalg.vector_norm(xc - r8.x) / torch.linalg.vector_norm(r8.x)) <= 1e-6
     # A is complex symmetric: -ksp_type cg -ksp_cg_type symmetric (COCG) applies
     resc = krylov.solve(A, bd, {"ksp_type": "cg", "ksp_cg_type": "symmetric", "pc_type": "jacobi",
                                 "ksp_rtol": 1e-12, "ksp_max_it": 20000})
