@@ -12,7 +12,6 @@ import os
 import sys
 import time
 
-import numpy as np
 
 
 def _rank() -> int:

@@ -3,9 +3,7 @@
 import argparse
 import os
 import sys
-import time
 
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
