@@ -153,6 +153,9 @@ class Solver():
             # host numpy on every rank (b is replicated), like the reference's serial loops
             from . import mt
             rows = self.boundaries.array.real
+            if rows.shape[1] != 53 + self.dofs.shape[1]:
+                Print.master('     boundaryElements.dat is not consistent with the basis order')
+                exit(-1)
             za, zb = float(self.nodes[:, 2::3].max()), float(self.nodes[:, 2::3].min())  # solver.py:381-401
             pols = data_model.get('polarization')
             for tmp in pols:
