@@ -162,4 +162,4 @@ def unitary_test():
     """Unitary test for common.py script."""
 
 
-__all__ = ["Print", "InputParameters", "Timer", "Timers", "np"]
+__all__ = ["Print", "InputParameters", "Timer", "Timers"]

@@ -680,9 +680,7 @@ def solve_multi(A: CSRMatrix, B: torch.Tensor, options=None, ctx: DistContext = 
         return X, results
     if ksp == "cg" and str(o.get("ksp_cg_type", "symmetric")) != "symmetric":
         raise ValueError("A is complex symmetric, not Hermitian: use -ksp_cg_type symmetric")
-    pc = str(o.get("pc_type", "jacobi"))
-    if pc in ("sor", "bjacobi", "asm", "gamg", "lu", "ilu"):
-        pc = "jacobi"
+    pc = resolve_pc(o)
     op = Operator(A, pc=pc, ctx=ctx, halo="p2p" if ctx is not None and ctx.world > 1 else "auto")
     rtol, maxit = float(o.get("ksp_rtol", 1e-5)), int(o.get("ksp_max_it", 10000))
     for r0 in range(0, nrhs, 8):
@@ -712,15 +710,45 @@ def parse_petsc_options(path_or_text):
     return opts
 
 
+class UnsupportedSolverError(ValueError):
+    """The options file asks for a solve this backend does not provide (direct factorisations)."""
+
+
+# -pc_type values of the reference's shipped option files (examples/case*/petsc.opts, consumed by
+# setFromOptions at solver.py:586-589) that have no counterpart here and what stands in for them
+_PC_SUBSTITUTES = {"sor": "jacobi", "bjacobi": "jacobi", "asm": "jacobi", "gamg": "jacobi", "ilu": "jacobi",
+                   "icc": "jacobi", "eisenstat": "jacobi"}
+_PC_DIRECT = ("lu", "cholesky", "svd")
+
+
+def resolve_pc(options, notify=None):
+    """-pc_type of the options file -> preconditioner of this backend.  Every substitution is announced on
+    the master rank (`notify`, default Print.master); a direct factorisation (-pc_type lu/cholesky, usually
+    with -ksp_type preonly: examples/case4/petsc.opts) is refused, there is no direct solver here."""
+    if notify is None:
+        from .common import Print
+        notify = Print.master
+    ksp = str(options.get("ksp_type", "gmres"))
+    pc = str(options.get("pc_type", "jacobi"))
+    if pc in _PC_DIRECT or ksp == "preonly":
+        raise UnsupportedSolverError(
+            "-ksp_type %s -pc_type %s asks for a direct factorisation (MUMPS/PETSc LU); the B200 backend has "
+            "iterative solvers only: use -ksp_type cr|cg|gmres|bcgs|tfqmr with -pc_type jacobi" % (ksp, pc))
+    if pc in _PC_SUBSTITUTES:
+        sub = _PC_SUBSTITUTES[pc]
+        notify("     -pc_type %s is not available on the B200 backend: using -pc_type %s instead "
+               "(iteration counts will differ from the reference's)" % (pc, sub))
+        pc = sub
+    return pc
+
+
 def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, monitor=None) -> SolveResult:
-    """KSP front end: ksp_type gmres|bcgs|tfqmr|cg (symmetric)|cr, pc_type none|jacobi (sor is mapped to jacobi
-    with a warning: PETSc's SOR sweep is sequential), ksp_rtol,
-    ksp_gmres_restart, ksp_max_it."""
+    """KSP front end: ksp_type gmres|bcgs|tfqmr|cg (symmetric)|cr, pc_type none|jacobi, ksp_rtol,
+    ksp_gmres_restart, ksp_max_it.  Other -pc_type values of the reference's option files are replaced
+    with a printed notice (resolve_pc); direct solves (-pc_type lu, -ksp_type preonly) raise."""
     o = dict(options or {})
     ksp = str(o.get("ksp_type", "gmres"))
-    pc = str(o.get("pc_type", "jacobi"))
-    if pc in ("sor", "bjacobi", "asm", "gamg", "lu", "ilu"):
-        pc = "jacobi"
+    pc = resolve_pc(o)
     rtol = float(o.get("ksp_rtol", 1e-5))  # PETSc default when the file does not set it
     maxit = int(o.get("ksp_max_it", 10000))
     op = Operator(A, pc=pc, ctx=ctx)

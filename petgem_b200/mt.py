@@ -4,7 +4,7 @@ Mirrors what ``petgem/solver.py:318-512`` does for ``mode: mt``: a 1-D finite-el
 layered-earth problem along z gives the excitation on the four lateral sides and the top of the box
 (``petgem/mt1d.py:21-76``), and every boundary face contributes the surface integral of the
 tangential basis functions against that field (Neumann condition), integrated with a symmetric
-triangle rule of degree 2p.  Vectorised numpy on rank 0, like the reference's serial loops; the
+triangle rule of degree 2p.  Vectorised numpy, evaluated on every rank (b is replicated); the
 two polarizations then share the matrix and are solved in lockstep (``krylov.solve_multi``).
 """
 from __future__ import annotations

@@ -3,8 +3,8 @@
 Produces exactly the scratch files ``Solver.setup`` reads, in PETSc
 binary format, from a Gmsh 2.2 ASCII mesh -- without meshio/h5py/petsc4py (absent here).
 Topology and numbering come from ``petgem_b200.mesh`` / ``hvfem`` (bit-identical to the
-reference).  MT boundary-element tables (preprocessing.py:314-381) are not produced:
-outside the hot path.
+reference), including the MT boundary-element table ``boundaryElements.dat``
+(preprocessing.py:314-381) that feeds the MT right-hand side.
 """
 from __future__ import annotations
 

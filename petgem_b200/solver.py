@@ -212,20 +212,28 @@ class Solver():
                 xi = torch.cat([full[r * ctx.max_rows:r * ctx.max_rows + ctx.sizes[r]] for r in range(ctx.world)])
             return xi[perm] if perm is not None else xi
 
-        if num_polarizations > 1:
-            # the right-hand sides share A (the two MT polarizations): one pass over the matrix per
-            # iteration for all of them when the solver type allows it (krylov.solve_multi)
-            B = torch.stack([to_internal(self.b[i].t)[lo:hi] for i in np.arange(num_polarizations)], dim=1).contiguous()
-            X, results = krylov.solve_multi(self.A.csr, B, self.petsc_options, ctx=ctx)   # solver.py:589
-            self.ksp_results = list(results)
-            xs = [X[:, i].contiguous() for i in range(num_polarizations)]
-        else:
-            res = krylov.solve(self.A.csr, to_internal(self.b[0].t)[lo:hi].contiguous(), self.petsc_options,
-                               ctx=ctx)                                                     # solver.py:589
-            self.ksp_results.append(res)
-            if not res.converged:
-                Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
-            xs = [res.x]
+        try:
+            if num_polarizations > 1:
+                # the right-hand sides share A (the two MT polarizations): one pass over the matrix per
+                # iteration for all of them when the solver type allows it (krylov.solve_multi)
+                B = torch.stack([to_internal(self.b[i].t)[lo:hi] for i in np.arange(num_polarizations)],
+                                dim=1).contiguous()
+                X, results = krylov.solve_multi(self.A.csr, B, self.petsc_options, ctx=ctx)   # solver.py:589
+                self.ksp_results = list(results)
+                for res in results:
+                    if not np.all(res.converged):
+                        Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
+                xs = [X[:, i].contiguous() for i in range(num_polarizations)]
+            else:
+                res = krylov.solve(self.A.csr, to_internal(self.b[0].t)[lo:hi].contiguous(), self.petsc_options,
+                                   ctx=ctx)                                                     # solver.py:589
+                self.ksp_results.append(res)
+                if not res.converged:
+                    Print.master('     KSP did not converge: %s after %d iterations' % (res.reason, res.iterations))
+                xs = [res.x]
+        except krylov.UnsupportedSolverError as err:
+            Print.master('     ' + str(err))
+            exit(-1)
         for i in np.arange(num_polarizations):
             self.x[i].t.copy_(collect(xs[i]))
             if parEnv.rank == 0:
