@@ -275,6 +275,27 @@ int pg_krylov_solve(int64_t n, const int64_t *rowptr, const int32_t *colidx, con
                     double *x, int method, int jacobi, double rtol, int maxit, int check_every, void *work,
                     int *iterations, double *rel_residual, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Gradient-space (Hiptmair) preconditioner, the GPU-friendly stand-in for the -pc_type sor / asm /
+ * gamg of the reference's option files (examples/case1..5 petsc.opts, read by KSP.setFromOptions at
+ * solver.py:586-589):  M^-1 = D^-1 + G diag(G^T A G)^-1 G^T, G = discrete gradient of the H1 vertex
+ * (and, p >= 2, quadratic edge) functions in the Nedelec dofs, a REAL sparse matrix with <= 3 entries
+ * per row.  Complex symmetric, so COCG / COCR stay valid.  petgem_b200/gradient.py builds G.
+ * --------------------------------------------------------------------------- */
+/* Y[i,:] = s[i] * (sum_j vals[j] X[colidx[j],:]) + a[i] * Z[i,:] for a real CSR matrix (rowptr i32 [rows+1],
+ * colidx i32, vals f64) and k interleaved complex vectors (k = 1, 2, 4, 8).  s, a: complex [rows] or NULL
+ * (s NULL: factor 1; a NULL: no Z term). */
+int pg_rcsr_apply(int64_t rows, const int32_t *rowptr, const int32_t *colidx, const double *vals, int k,
+                  const double *X, const double *s, const double *a, const double *Z, double *Y, void *stream);
+/* out[k] = sum_{i < a_rows} sum_j R[k,i] A[i,j] R[k,j]: diagonal of R A R^T restricted to the owned rows of A
+ * (R = G^T as real CSR with columns sorted, indexed like the columns of A; A complex CSR, a_rows owned rows).
+ * On several GPUs the partial sums of the ranks add up to diag(G^T A G). */
+int pg_galerkin_diagonal(int64_t rows, const int32_t *r_rowptr, const int32_t *r_colidx, const double *r_vals,
+                         int64_t a_rows, const int64_t *a_rowptr, const int32_t *a_colidx, const double *a_vals,
+                         double *out, void *stream);
+/* d[i] = 1/d[i] (complex), 0 where d[i] == 0 or mask[i] == 0 (mask u8 [n] or NULL) */
+int pg_masked_reciprocal(int64_t n, const uint8_t *mask, double *d, void *stream);
+
 /* CUDA graph of a batch of the calls above (the launches of the Krylov iterations between two host
  * checks of the residual): begin capture on a NON-default stream, issue the calls, end -> executable
  * graph, launch it any number of times. */

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -22,29 +22,60 @@ NVCC_FLAGS = [
 ]
 
 
+LINK_LIBS = []
+
+
 class PetgemB200Error(RuntimeError):
     """A C-ABI call returned a non-zero status."""
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _newer(path: str, deps) -> bool:
+    """True if `path` is missing or older than any of `deps`."""
+    if not os.path.exists(path):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    built = os.path.getmtime(path)
     return any(os.path.getmtime(d) > built for d in deps)
 
 
+def _stale() -> bool:
+    return _newer(LIB_PATH, [os.path.join(CSRC, f) for f in SOURCES + HEADERS])
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into petgem_b200/libpetgem_b200.so."""
+    """Compile every CUDA source for sm_100a into petgem_b200/libpetgem_b200.so: one object per source
+    (compiled in parallel, rebuilt only when the source or a header changed), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, h) for h in HEADERS]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if force or _newer(obj, [path] + headers):
+            cmd = [nvcc] + compile_flags + ["-c", "-o", obj, path]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + LINK_LIBS
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -115,6 +146,9 @@ SIGNATURES = {
     "pg_krylov_workspace_bytes": (_i64, [_i64]),
     "pg_krylov_solve": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i32, _i32, _d, _i32, _i32, _p, C.POINTER(C.c_int),
                                   C.POINTER(C.c_double), _p]),
+    "pg_rcsr_apply": (C.c_int, [_i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "pg_galerkin_diagonal": (C.c_int, [_i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "pg_masked_reciprocal": (C.c_int, [_i64, _p, _p, _p]),
     "pg_graph_begin": (C.c_int, [_p]),
     "pg_graph_end": (C.c_int, [_p, C.POINTER(_p)]),
     "pg_graph_launch": (C.c_int, [_p, _p]),

@@ -90,7 +90,9 @@ class InputParameters(object):
         else:
             if rank == 0:
                 os.makedirs(self.output["directory_scratch"], exist_ok=True)
-            self.output["remove_scratch"] = True
+            # common.py:343-352 always removes a user-given scratch directory after the run; an explicit
+            # `remove_scratch: False` in the output section keeps it (x{i}.dat stay readable)
+            self.output["remove_scratch"] = self.output.get("remove_scratch", True) is not False
 
     def _verify(self, mode, data):
         sigma = data.get("sigma")

@@ -254,18 +254,39 @@ class AssemblyPlan:
         """bd_entity: [nEnt] uint8 (device tensor or host array) or None."""
         if bd_entity is None:
             check(lib().pg_plan_set_dirichlet(self._h, None, None, None, stream_ptr()), "pg_plan_set_dirichlet")
+            self.bd_entity = None
             return
         t = torch.as_tensor(bd_entity, dtype=torch.uint8).to(self.elems.device).contiguous()
         if t.numel() != self.nEnt:
             raise ValueError("bd_entity must have %d entries" % self.nEnt)
+        self.bd_entity = t
         check(
             lib().pg_plan_set_dirichlet(self._h, ptr(self.elems.elemsE), ptr(self.elems.elemsF), ptr(t), stream_ptr()),
             "pg_plan_set_dirichlet",
         )
 
+    def dirichlet_row_mask(self):
+        """uint8 [N] in the numbering in use: rows of the Dirichlet entities given to set_dirichlet
+        (all dofs of boundary edges and faces, mesh.py:280-321); None without Dirichlet entities."""
+        bd = getattr(self, "bd_entity", None)
+        if bd is None:
+            return None
+        el, p = self.elems, self.p
+        nE, nF, nf = el.nEdges, el.nFaces, p * (p - 1)
+        ref = torch.zeros((self.N,), dtype=torch.uint8, device=el.device)
+        ref[: nE * p] = bd[:nE].repeat_interleave(p)
+        if p >= 2:
+            ref[nE * p: nE * p + nF * nf] = bd[nE: nE + nF].repeat_interleave(nf)
+        if self.order_host is None:
+            return ref
+        out = torch.empty_like(ref)
+        out[self.dof_permutation().to(torch.int64)] = ref
+        return out
+
     def assemble(self, geo, code, omega, mu=MU0, apply_dirichlet=False, diag=1.0, out=None):
         """Numeric phase -> vals [nnz] complex128."""
         dev = self.elems.device
+        self.dirichlet_applied = bool(apply_dirichlet)
         vals = out if out is not None else torch.empty((max(self.nnz, 1),), dtype=torch.complex128, device=dev)[: self.nnz]
         check(
             lib().pg_assemble(self._h, ptr(geo), ptr(code), ptr(element_table(self.p, dev)), -omega * mu,
@@ -291,6 +312,10 @@ class CSRMatrix:
         if blocked is None:
             blocked = os.environ.get("PG_SPMV_BLOCKED", "1") == "1"
         self.plan_ref = plan if (plan is not None and plan.p == 2) else None  # entity blocks of this matrix
+        self.asm_plan = plan  # mesh + numbering behind this matrix (gradient-space preconditioner)
+        # rows fixed by MatZeroRowsColumns, uint8 [N] in the numbering in use (None: no Dirichlet rows)
+        self.dirichlet_mask = plan.dirichlet_row_mask() if (plan is not None and getattr(plan, "dirichlet_applied",
+                                                                                         False)) else None
         self.plan = self.plan_ref if blocked else None
         self.colstart = colstart  # None = the plan's own global column starts
 
@@ -351,6 +376,7 @@ class CSRMatrix:
         mask = torch.zeros((self.N,), dtype=torch.uint8, device=self.vals.device)
         idx = torch.as_tensor(np.asarray(bd_rows, dtype=np.int64), device=self.vals.device)
         mask[idx] = 1
+        self.dirichlet_mask = mask if self.dirichlet_mask is None else (self.dirichlet_mask | mask)
         check(
             lib().pg_zero_rows_columns(self.rows, self.row_begin, ptr(self.rowptr), ptr(self.colidx), ptr(mask),
                                        float(diag), ptr(self.vals), stream_ptr()),

@@ -122,11 +122,18 @@ class Operator:
         dev = A.vals.device
         self.pc = pc
         self.inv_diag = None
-        if pc == "jacobi":
+        self.grad = None  # GradientSpace of the Hiptmair preconditioner
+        if pc in ("jacobi", "hiptmair"):
             d = A.diagonal()
             self.inv_diag = torch.where(d == 0, torch.ones_like(d), 1.0 / d)  # PCJACOBI: zero diagonal -> 1
         elif pc != "none":
-            raise ValueError("unsupported preconditioner %r (none, jacobi)" % pc)
+            raise ValueError("unsupported preconditioner %r (none, jacobi, hiptmair)" % pc)
+        if pc == "hiptmair":
+            if getattr(A, "asm_plan", None) is None:
+                raise ValueError("-pc_type hiptmair needs the mesh behind the matrix: build the CSRMatrix with "
+                                 "plan=AssemblyPlan(...)")
+            if halo == "auto" and ctx is not None and ctx.world > 1:
+                halo = "p2p"  # the gradient space is built in the [own | halo] numbering of the neighbour halo
         self.mode = "single"
         if ctx is not None and ctx.world > 1:
             # x exchange before the SpMV: neighbour halo (packed all_to_all) when the off-block column
@@ -153,6 +160,15 @@ class Operator:
                 cs = ctx.remap_columns(A.plan.column_starts()) if A.plan is not None else None
                 self.A_halo = CSRMatrix(A.rowptr, self.colidx_local, A.vals, ctx.world * ctx.max_rows, A.row_begin,
                                         plan=A.plan, colstart=cs, blocked=A.plan is not None)
+        if pc == "hiptmair":
+            from .gradient import GradientSpace
+
+            if self.mode == "allgather":
+                raise ValueError("-pc_type hiptmair needs the neighbour halo (halo='p2p')")
+            dist_run = self.mode == "p2p"
+            self.grad = GradientSpace(A.asm_plan, dirichlet_rows=A.dirichlet_mask, ctx=ctx if dist_run else None,
+                                      halo_ext=ctx._halo_ext if dist_run else None)
+            self.grad.setup(self.A_halo if dist_run else A)
         self.spmv_calls = 0
 
     def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
@@ -188,15 +204,27 @@ class Operator:
         return Y
 
     def precond(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """y = M^-1 x for a vector [n] or an interleaved block [n, k] (x and y must not alias for hiptmair)."""
+        if self.grad is not None:
+            return self.grad.apply(x, self.inv_diag, y)
         if self.inv_diag is None:
             if y.data_ptr() != x.data_ptr():
                 y.copy_(x)
+        elif x.dim() == 2:
+            check(lib().pg_zbscale_rows(self.n, int(x.shape[1]), ptr(self.inv_diag), ptr(x), ptr(y), stream_ptr()),
+                  "pg_zbscale_rows")
         else:
             check(lib().pg_zpointwise_mult(self.n, ptr(x), ptr(self.inv_diag), ptr(y), stream_ptr()), "pg_zpointwise_mult")
         return y
 
     def apply(self, x, y, tmp=None):
-        """y = M^-1 (A x); the Jacobi scaling rides in the SpMV epilogue."""
+        """y = M^-1 (A x); the Jacobi scaling rides in the SpMV epilogue, the gradient-space term of the
+        Hiptmair preconditioner needs A x as a whole first (tmp)."""
+        if self.grad is not None:
+            if tmp is None:
+                tmp = torch.empty_like(y)
+            self.matvec(x, tmp)
+            return self.grad.apply(tmp, self.inv_diag, y)
         return self.matvec(x, y, self.inv_diag)
 
 
@@ -544,10 +572,10 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
         if ctx is not None:
             ctx.allreduce(t)
 
-    if op.inv_diag is not None:
-        check(L.pg_zbscale_rows(n, k, ptr(op.inv_diag), ptr(R), ptr(Z), st()), "pg_zbscale_rows")
-    else:
-        Z.copy_(R)
+    general = op.grad is not None  # preconditioner that is not a row scaling: explicit M^-1 applications
+    dinv = None if general else op.inv_diag
+    MQ = Z_() if general else None
+    op.precond(R, Z)
     check(L.pg_zbnrm2sq(n, k, ptr(Z), ptr(out2), ptr(work), st()), "pg_zbnrm2sq")
     reduce_(out2[:k])
     bnorm = out2[:k].real.sqrt().cpu().numpy()
@@ -571,11 +599,15 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
     def iterations_cocr(count):
         cur = 0
         for _ in range(count):
-            check(L.pg_zbdotu_w(n, k, ptr(Q), ptr(Q), ptr(op.inv_diag), ptr(pq), ptr(work), st()), "pg_zbdotu_w")
+            if general:   # MQ = M^-1 (A p), then the same recurrences with the row scaling dropped
+                op.precond(Q, MQ)
+                check(L.pg_zbdotu(n, k, ptr(Q), ptr(MQ), ptr(pq), ptr(work), st()), "pg_zbdotu")
+            else:
+                check(L.pg_zbdotu_w(n, k, ptr(Q), ptr(Q), ptr(dinv), ptr(pq), ptr(work), st()), "pg_zbdotu_w")
             reduce_(pq)
             check(L.pg_zbdiv(k, ptr(rho[cur]), ptr(pq), ptr(alpha2), st()), "pg_zbdiv")
-            check(L.pg_cocr_update(n, k, ptr(alpha2), ptr(P), ptr(Q), ptr(op.inv_diag), ptr(X), ptr(Z), st()),
-                  "pg_cocr_update")
+            check(L.pg_cocr_update(n, k, ptr(alpha2), ptr(P), ptr(MQ if general else Q), ptr(dinv), ptr(X), ptr(Z),
+                                   st()), "pg_cocr_update")
             op.matmat(Z, AR)
             check(L.pg_zbdotu(n, k, ptr(Z), ptr(AR), ptr(rho[cur ^ 1]), ptr(work), st()), "pg_zbdotu")
             reduce_(rho[cur ^ 1])
@@ -595,8 +627,15 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
             check(L.pg_zbdotu(n, k, ptr(P), ptr(Q), ptr(pq), ptr(work), st()), "pg_zbdotu")
             reduce_(pq)
             check(L.pg_zbdiv(k, ptr(rho[cur]), ptr(pq), ptr(alpha2), st()), "pg_zbdiv")
-            check(L.pg_cocg_step(n, k, ptr(alpha2), ptr(P), ptr(Q), ptr(op.inv_diag), ptr(X), ptr(R), ptr(Z),
-                                 ptr(out2), ptr(work), st()), "pg_cocg_step")
+            if general:   # x += alpha p, r -= alpha q, z = M^-1 r, rho' = r^T z, |z|^2
+                check(L.pg_zbaxpy(n, k, ptr(alpha2), ptr(P), ptr(X), st()), "pg_zbaxpy")
+                check(L.pg_zbaxpy(n, k, ptr(alpha2[k:]), ptr(Q), ptr(R), st()), "pg_zbaxpy")
+                op.precond(R, Z)
+                check(L.pg_zbdotu(n, k, ptr(R), ptr(Z), ptr(out2), ptr(work), st()), "pg_zbdotu")
+                check(L.pg_zbnrm2sq(n, k, ptr(Z), ptr(out2[k:]), ptr(work), st()), "pg_zbnrm2sq")
+            else:
+                check(L.pg_cocg_step(n, k, ptr(alpha2), ptr(P), ptr(Q), ptr(dinv), ptr(X), ptr(R), ptr(Z),
+                                     ptr(out2), ptr(work), st()), "pg_cocg_step")
             reduce_(out2)
             rho[cur ^ 1].copy_(out2[:k])
             check(L.pg_zbdiv(k, ptr(rho[cur ^ 1]), ptr(rho[cur]), ptr(beta2), st()), "pg_zbdiv")
@@ -680,7 +719,7 @@ def solve_multi(A: CSRMatrix, B: torch.Tensor, options=None, ctx: DistContext = 
         return X, results
     if ksp == "cg" and str(o.get("ksp_cg_type", "symmetric")) != "symmetric":
         raise ValueError("A is complex symmetric, not Hermitian: use -ksp_cg_type symmetric")
-    pc = resolve_pc(o)
+    pc = resolve_pc(o, have_mesh=getattr(A, "asm_plan", None) is not None)
     op = Operator(A, pc=pc, ctx=ctx, halo="p2p" if ctx is not None and ctx.world > 1 else "auto")
     rtol, maxit = float(o.get("ksp_rtol", 1e-5)), int(o.get("ksp_max_it", 10000))
     for r0 in range(0, nrhs, 8):
@@ -716,12 +755,11 @@ class UnsupportedSolverError(ValueError):
 
 # -pc_type values of the reference's shipped option files (examples/case*/petsc.opts, consumed by
 # setFromOptions at solver.py:586-589) that have no counterpart here and what stands in for them
-_PC_SUBSTITUTES = {"sor": "jacobi", "bjacobi": "jacobi", "asm": "jacobi", "gamg": "jacobi", "ilu": "jacobi",
-                   "icc": "jacobi", "eisenstat": "jacobi"}
+_PC_SUBSTITUTES = ("sor", "bjacobi", "asm", "gamg", "ilu", "icc", "eisenstat", "hypre", "ml")
 _PC_DIRECT = ("lu", "cholesky", "svd")
 
 
-def resolve_pc(options, notify=None):
+def resolve_pc(options, notify=None, have_mesh=True):
     """-pc_type of the options file -> preconditioner of this backend.  Every substitution is announced on
     the master rank (`notify`, default Print.master); a direct factorisation (-pc_type lu/cholesky, usually
     with -ksp_type preonly: examples/case4/petsc.opts) is refused, there is no direct solver here."""
@@ -735,7 +773,9 @@ def resolve_pc(options, notify=None):
             "-ksp_type %s -pc_type %s asks for a direct factorisation (MUMPS/PETSc LU); the B200 backend has "
             "iterative solvers only: use -ksp_type cr|cg|gmres|bcgs|tfqmr with -pc_type jacobi" % (ksp, pc))
     if pc in _PC_SUBSTITUTES:
-        sub = _PC_SUBSTITUTES[pc]
+        # strongest preconditioner of this backend: Hiptmair's hybrid smoother when the mesh behind the
+        # matrix is known (gradient.py), point Jacobi for a bare CSR matrix
+        sub = "hiptmair" if have_mesh else "jacobi"
         notify("     -pc_type %s is not available on the B200 backend: using -pc_type %s instead "
                "(iteration counts will differ from the reference's)" % (pc, sub))
         pc = sub
@@ -743,12 +783,12 @@ def resolve_pc(options, notify=None):
 
 
 def solve(A: CSRMatrix, b: torch.Tensor, options=None, ctx: DistContext = None, monitor=None) -> SolveResult:
-    """KSP front end: ksp_type gmres|bcgs|tfqmr|cg (symmetric)|cr, pc_type none|jacobi, ksp_rtol,
+    """KSP front end: ksp_type gmres|bcgs|tfqmr|cg (symmetric)|cr, pc_type none|jacobi|hiptmair, ksp_rtol,
     ksp_gmres_restart, ksp_max_it.  Other -pc_type values of the reference's option files are replaced
     with a printed notice (resolve_pc); direct solves (-pc_type lu, -ksp_type preonly) raise."""
     o = dict(options or {})
     ksp = str(o.get("ksp_type", "gmres"))
-    pc = resolve_pc(o)
+    pc = resolve_pc(o, have_mesh=getattr(A, "asm_plan", None) is not None)
     rtol = float(o.get("ksp_rtol", 1e-5))  # PETSc default when the file does not set it
     maxit = int(o.get("ksp_max_it", 10000))
     op = Operator(A, pc=pc, ctx=ctx)

@@ -2,8 +2,8 @@
 
 ``fieldInterpolator`` follows postprocessing.py:479-616 (locate receivers, evaluate the basis at
 the receiver, E = sum_j x_j N_j, H = sum_j x_j curl N_j / (i omega mu)), vectorised with the
-product's basis tables; output is ``<directory>/fields.npz`` (+ ``.h5`` when h5py exists)
-instead of the reference's HDF5/VTK writers (out of scope).
+product's basis tables; output is ``<directory>/fields.npz``; the scratch files are removed afterwards
+like the reference does (postprocessing.py:463-472) unless the parameter file says ``remove_scratch: False``.
 """
 from __future__ import annotations
 
@@ -92,6 +92,16 @@ class Postprocessing():
             out['run_time_s'] = Timers().elapsed('Assembly') + Timers().elapsed('Solver')
             np.savez(inputSetup.output.get('directory') + '/fields.npz', **out)
             self.fields = out
+            # scratch clean-up (postprocessing.py:463-472): the whole scratch directory when it was given
+            # in the parameter file, else only the PETSc binary files written next to the results
+            import os
+            import shutil
+            if inputSetup.output.get('remove_scratch'):
+                shutil.rmtree(out_dir, ignore_errors=True)
+            elif os.path.abspath(out_dir) == os.path.abspath(inputSetup.output.get('directory')):
+                for name in os.listdir(out_dir):
+                    if name.endswith('.dat') or name.endswith('.info'):
+                        os.remove(os.path.join(out_dir, name))
         Timers()["Postprocessing"].stop()
 
 

@@ -112,6 +112,8 @@ class Solver():
             self.row_begins = [0] + [self.plan.entity_aligned_row(N * r // world) for r in range(1, world)]
             ends = self.row_begins[1:] + [N]
             order_host = self.plan.order_host if self.plan.order_host is not None else 'reference'
+            self.plan = None  # release the global symbolic plan before the owned-rows plan is built
+            torch.cuda.empty_cache()
             self.plan = AssemblyPlan(self.elems, basis_order, order=order_host,
                                      row_range=(self.row_begins[parEnv.rank], ends[parEnv.rank]))
         geo, code = self.elems.geometry(self.plan.element_range)

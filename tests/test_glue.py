@@ -44,6 +44,7 @@ output:
   vtk: False
   directory: %(out)s
   directory_scratch: %(tmp)s
+  remove_scratch: False
 """
 
 
@@ -147,7 +148,8 @@ def test_kernel_cli_two_ranks_match_one(tmp_path, topo):
         d = tmp_path / ("w%d" % world)
         d.mkdir()
         params, opts = make_case(d, topo, nord=2)
-        open(opts, "w").write("-ksp_type cg\n-ksp_cg_type symmetric\n-pc_type jacobi\n-ksp_rtol 1e-11\n-ksp_max_it 40000\n")
+        # -pc_type sor (the reference's shipped choice) -> Hiptmair preconditioner, distributed over the ranks
+        open(opts, "w").write("-ksp_type cr\n-pc_type sor\n-ksp_rtol 1e-11\n-ksp_max_it 40000\n")
         cmd = [sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params]
         if world > 1:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
@@ -157,6 +159,38 @@ def test_kernel_cli_two_ranks_match_one(tmp_path, topo):
         fields.append(np.load(str(d / "out" / "fields.npz"))["fields_0"])
     scale = np.abs(fields[0][:, :3]).max()
     assert np.abs(fields[0][:, :3] - fields[1][:, :3]).max() <= 1e-6 * scale
+    gold = golden("test_mesh_fields_p2.npz")["fields"]
+    for f in fields:
+        assert np.abs(f[:, :3] - gold[:, :3]).max() <= 1e-6 * np.abs(gold[:, :3]).max()
+
+
+@pytest.mark.gpu
+def test_kernel_cli_p2_with_the_shipped_solver_options(tmp_path, topo):
+    """kernel.py at p = 2 with the solver options PETGEM ships (examples/case1/petsc.opts: gmres + sor, tight
+    rtol here): the SOR request is announced as replaced by the Hiptmair preconditioner and the receiver
+    fields match the golden fields of the reference pipeline (oracle/make_golden_fields.py) to 1e-6."""
+    params, opts = make_case(tmp_path, topo, nord=2)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params],
+                         capture_output=True, text=True, timeout=1200)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "-pc_type sor is not available" in res.stdout and "hiptmair" in res.stdout
+    F = np.load(str(tmp_path / "out" / "fields.npz"))["fields_0"]
+    gold = golden("test_mesh_fields_p2.npz")["fields"]
+    assert np.abs(F[:, :3] - gold[:, :3]).max() <= 1e-6 * np.abs(gold[:, :3]).max()
+    assert np.abs(F[:, 3:] - gold[:, 3:]).max() <= 1e-6 * np.abs(gold[:, 3:]).max()
+
+
+@pytest.mark.gpu
+def test_kernel_cli_refuses_direct_solver_options(tmp_path, topo):
+    """-ksp_type preonly -pc_type lu (examples/case4/petsc.opts, MUMPS) has no counterpart: fail loudly, do
+    not silently iterate."""
+    params, opts = make_case(tmp_path, topo, nord=1)
+    open(opts, "w").write("-ksp_type preonly\n-pc_type lu\n-pc_factor_mat_solver_type mumps\n")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "kernel.py"), "-options_file", opts, params],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode != 0
+    assert "direct factorisation" in res.stdout
+    assert not os.path.exists(str(tmp_path / "tmp" / "x0.dat"))
 
 
 @pytest.mark.gpu
@@ -221,6 +255,7 @@ output:
   vtk: False
   directory: %(out)s
   directory_scratch: %(tmp)s
+  remove_scratch: False
 """
 
 

@@ -181,3 +181,25 @@ def test_batched_orientation_equals_reference_table(topo):
                                                    topo["facesE"][topo["elemsF"]])
     assert np.array_equal(eo, topo["orient"][:, :6]) and np.array_equal(fo, topo["orient"][:, 6:])
     assert len(set(map(int, fo.reshape(-1)))) == 6  # all six face codes occur on this mesh
+
+
+def test_pc_substitution_is_announced_and_direct_solves_refused():
+    """-pc_type values of the reference's option files that have no counterpart are replaced with a notice;
+    direct factorisations raise (no silent rewriting)."""
+    from petgem_b200 import krylov
+
+    said = []
+    assert krylov.resolve_pc({"ksp_type": "gmres", "pc_type": "sor"}, notify=said.append) == "hiptmair"
+    assert len(said) == 1 and "sor" in said[0] and "hiptmair" in said[0]
+    assert krylov.resolve_pc({"pc_type": "gamg"}, notify=said.append, have_mesh=False) == "jacobi"
+    assert krylov.resolve_pc({"pc_type": "jacobi"}, notify=said.append) == "jacobi" and len(said) == 2
+    for bad in ({"ksp_type": "preonly", "pc_type": "lu"}, {"pc_type": "cholesky"}, {"ksp_type": "preonly"}):
+        with pytest.raises(krylov.UnsupportedSolverError):
+            krylov.resolve_pc(bad, notify=said.append)
+
+
+def test_common_star_import():
+    """`from petgem.common import *` is the reference's import style (solver.py:16)."""
+    ns = {}
+    exec("from petgem_b200.common import *", ns)
+    assert "Print" in ns and "InputParameters" in ns and "Timers" in ns

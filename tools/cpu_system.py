@@ -86,14 +86,14 @@ def test_mesh_case(p):
     return z, A, b, dofs, bd, info
 
 
-def kuhn_case(m, p):
+def kuhn_case(m, p, length=3500.0):
     from petgem_b200 import synthetic
 
-    nodes, elemsN = synthetic.kuhn_box(m)
+    nodes, elemsN = synthetic.kuhn_box(m, length=length)
     tab = synthetic.mesh_tables(nodes, elemsN)
     sigma = synthetic.layered_sigma(nodes, elemsN)
     A, dofs, bd, info = build_system(tab, sigma, p)
-    b = csem_rhs(tab, dofs, p, info["N"], np.array([1750.0, 1750.0, -975.0]), bd=bd)
+    b = csem_rhs(tab, dofs, p, info["N"], np.array([0.5, 0.5, -0.28]) * length, bd=bd)
     return tab, A, b, dofs, bd, info
 
 
