@@ -305,6 +305,27 @@ def time_to_solution(dev, m=55, p=1, maxit=20000):
 _REAL_STDOUT = None
 
 
+def make_plan(el, p, order, world, rank):
+    """Symbolic plan of this rank: the whole matrix on one GPU, else a PETSc-style contiguous row block
+    (entity aligned) -> (plan, row_begins)."""
+    import torch
+
+    from petgem_b200.device import AssemblyPlan
+
+    if world == 1:
+        return AssemblyPlan(el, p, order=order), [0]
+    probe = AssemblyPlan(el, p, order=order)  # global plan: entity-aligned PETSc-style split
+    N = probe.N
+    row_begins = [0] + [probe.entity_aligned_row(N * r // world) for r in range(1, world)]
+    order_host = probe.order_host
+    del probe
+    torch.cuda.empty_cache()
+    rb = row_begins[rank]
+    re_ = row_begins[rank + 1] if rank + 1 < world else N
+    plan = AssemblyPlan(el, p, order=order_host if order_host is not None else "reference", row_range=(rb, re_))
+    return plan, row_begins
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
     data = (json.dumps(line) + "\n").encode()
@@ -377,19 +398,7 @@ def main():
     el = ElementData(rows["nodes"], rows["elemsN"], rows["elemsE"], rows["edgesNodes"], rows["facesEdges"],
                      rows["elemsF"], rows["sigma"], tab["nEdges"], tab["nFaces"], device=dev)
     t0 = time.time()
-    if world == 1:
-        plan = AssemblyPlan(el, p, order=args.order)
-        row_begins = [0]
-    else:
-        probe = AssemblyPlan(el, p, order=args.order)  # global plan: entity-aligned PETSc-style split
-        N = probe.N
-        row_begins = [0] + [probe.entity_aligned_row(N * r // world) for r in range(1, world)]
-        order_host = probe.order_host
-        del probe
-        torch.cuda.empty_cache()
-        rb = row_begins[rank]
-        re_ = row_begins[rank + 1] if rank + 1 < world else N
-        plan = AssemblyPlan(el, p, order=order_host if order_host is not None else "reference", row_range=(rb, re_))
+    plan, row_begins = make_plan(el, p, args.order, world, rank)
     plan.set_dirichlet(bd_entities(tab, p, plan.nEnt))
     rowptr, colidx = plan.csr()
     torch.cuda.synchronize()
