@@ -72,9 +72,25 @@ int pg_element_geometry(int64_t T, const double *nodes, const int32_t *elemsN, c
                         double *geo, uint32_t *code, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * a5 + a6: the geometry-independent half of computeElementalMatrices: shape3DETet (hvfem.py:319-464)
+ * and the quadrature (compute3DGaussPoints, hvfem.py:1055-1610) folded ONCE per order into the
+ * reference-element contraction table the element kernels read:
+ *   table [nexp,nexp,12] f64: per expanded pair (J,K) SK[6] then SM[6], packed (00,11,22,01,02,12),
+ *   S^{ab}_{JK} = int_master N_J^a N_K^b (+ b<->a for a != b), curls for SK; exact conical Gauss-Jacobi
+ *   rule of degree 2p+1.  pg_table_size(p) doubles; synchronous (scratch is freed on return).
+ * --------------------------------------------------------------------------- */
+int64_t pg_table_size(int p);
+int pg_tables_init(int p, double *table, void *stream);
+/* shape3DETet(X, Nord, NoriE, NoriF) (hvfem.py:319-464) at ONE master point, evaluated on the host by the
+ * same code the device kernels run (a host utility like pg_ndof_element, used to pin the C++ basis against
+ * the reference's golden shape functions without a GPU; no hot-path call goes through it):
+ *   code as written by pg_element_geometry; xi_host [3]; N_host, C_host [n,3] (function-major). */
+int pg_shape_functions_host(int p, uint32_t code, const double *xi_host, double *N_host, double *C_host);
+
+/* ---------------------------------------------------------------------------
  * a4 (+a5, a6): computeElementalMatrices (hvfem.py:223-316), batched.
  *   table [nexp,nexp,12] f64: per expanded pair (J,K) SK[6] then SM[6]
- *         (petgem_b200/basis.py:element_tables; built once per order)
+ *         (pg_tables_init; built once per order)
  *   Me, Ke [T,n,n] f64 row-major (either may be NULL)
  * --------------------------------------------------------------------------- */
 int pg_element_matrices(int64_t T, int p, const double *geo, const uint32_t *code, const double *table,
@@ -274,6 +290,31 @@ int64_t pg_krylov_workspace_bytes(int64_t n);
 int pg_krylov_solve(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *b,
                     double *x, int method, int jacobi, double rtol, int maxit, int check_every, void *work,
                     int *iterations, double *rel_residual, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * f1: the callers on either side of the solve, on the device.
+ * pg_locate_points: containing element of each point, lowest element index whose barycentric coordinates
+ *   are all >= -tol, -1 if none (postprocessing.py:532-539 / preprocessing.py:414-420 use
+ *   Delaunay.find_simplex on the mesh): points [npts,3] f64 -> pt_elem [npts] i32.  Synchronous.
+ * pg_interpolate_fields: fieldInterpolator (postprocessing.py:479-616): for every point the basis of its
+ *   element is evaluated at the point, E = sum_j x_j N_j, H = sum_j x_j curl N_j / (i omega mu):
+ *   fields [npts,6] complex128 (Ex,Ey,Ez,Hx,Hy,Hz); x [N] complex128; perm NULL: x in the reference dof
+ *   numbering, else perm[ref dof] = index into x (pg_plan_dof_permutation).  NaN where pt_elem < 0.
+ * pg_csem_rhs: the dipole right-hand side (solver.py:247-316): b[dof_j] += i omega mu (moment . N_j(x_src))
+ *   for the dofs of the source element; position/moment are HOST xyz triples (moment = current * length *
+ *   rotation(azimuth, dip), hvfem.py:2303-2344); b holds the rows [row_begin, row_begin+local_rows) of the
+ *   numbering in use (perm as above).  Synchronous.
+ * --------------------------------------------------------------------------- */
+int pg_locate_points(int64_t T, const double *nodes, int64_t npts, const double *points, double tol,
+                     int32_t *pt_elem, void *stream);
+int pg_interpolate_fields(int64_t npts, const double *points, const int32_t *pt_elem, int p, const double *nodes,
+                          const uint32_t *code, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges,
+                          int64_t nFaces, const int32_t *perm, const double *x, double omega, double mu, double *fields,
+                          void *stream);
+int pg_csem_rhs(int p, int64_t source_elem, const double *position_host, const double *moment_host, const double *nodes,
+                const uint32_t *code, const int32_t *elemsE, const int32_t *elemsF, int64_t nEdges, int64_t nFaces,
+                const int32_t *perm, int64_t row_begin, int64_t local_rows, double omega, double mu, double *b,
+                void *stream);
 
 /* ---------------------------------------------------------------------------
  * Gradient-space (Hiptmair) preconditioner, the GPU-friendly stand-in for the -pc_type sor / asm /

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu"]
-HEADERS = ["pg_common.cuh", "pg_plan.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu", "pg_tables.cu"]
+HEADERS = ["pg_common.cuh", "pg_plan.cuh", "pg_basis.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared",
@@ -146,6 +146,12 @@ SIGNATURES = {
     "pg_krylov_workspace_bytes": (_i64, [_i64]),
     "pg_krylov_solve": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i32, _i32, _d, _i32, _i32, _p, C.POINTER(C.c_int),
                                   C.POINTER(C.c_double), _p]),
+    "pg_table_size": (_i64, [_i32]),
+    "pg_tables_init": (C.c_int, [_i32, _p, _p]),
+    "pg_shape_functions_host": (C.c_int, [_i32, C.c_uint32, _p, _p, _p]),
+    "pg_locate_points": (C.c_int, [_i64, _p, _i64, _p, _d, _p, _p]),
+    "pg_interpolate_fields": (C.c_int, [_i64, _p, _p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _d, _d, _p, _p]),
+    "pg_csem_rhs": (C.c_int, [_i32, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _d, _d, _p, _p]),
     "pg_rcsr_apply": (C.c_int, [_i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "pg_galerkin_diagonal": (C.c_int, [_i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "pg_masked_reciprocal": (C.c_int, [_i64, _p, _p, _p]),

@@ -487,10 +487,12 @@ __device__ __forceinline__ void load_geo(const AsmArgs &a, int64_t t, double2 (&
     cd = __ldg(a.code + t);
 }
 
-// Finished tiles leave shared memory through the bulk-copy engine (cp.async.bulk shared -> global, SASS
-// UBLKCP) instead of an LDS + ST.CS loop through the load/store pipe, which ncu shows saturated (86 % of
-// l1tex data-pipe wavefronts, ~11 % of them this copy): the rows of an entity are contiguous in vals and in
-// the tile, so one lane issues one copy of R*L*16 bytes per entity.
+// BULK variant (PG_ASM_BULK=1): finished tiles leave shared memory through the bulk-copy engine
+// (cp.async.bulk shared -> global, SASS UBLKCP) instead of an LDS + ST.CS loop through the load/store pipe
+// (86 % of l1tex data-pipe wavefronts, ~11 % of them this copy): the rows of an entity are contiguous in vals
+// and in the tile, so one lane issues one copy of R*L*16 bytes per entity.  Measured at C3: LSU pipe 86 -> 74 %,
+// kernel 8.27 -> 8.45 ms (the fence + wait + syncs cost more than the loop; the kernel is issue/latency bound
+// at 4 warps per scheduler), so it is NOT the default.  Evidence: profiles/r2_assemble_small_bulk_ab.json.
 __device__ __forceinline__ void bulk_store_tile(double2 *gdst, const double2 *ssrc, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                  "cp.async.bulk.commit_group;"
@@ -711,7 +713,7 @@ static int launch_assemble_small(const pg_plan *pl, AsmArgs a, cudaStream_t st) 
     const size_t smem = table_bytes + (size_t)groups * per_group;
     static const bool bulk = [] {
         const char *e = getenv("PG_ASM_BULK");
-        return e ? atoi(e) != 0 : true;
+        return e ? atoi(e) != 0 : false;  // measured 2 % slower at C3 (profiles/r2_assemble_small_bulk_ab.json)
     }();
     auto kern = bulk ? assemble_small_kernel<P, true> : assemble_small_kernel<P, false>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -34,12 +34,49 @@ _TABLE_CACHE = {}
 
 
 def element_table(p: int, device=None) -> torch.Tensor:
-    """Reference-element contraction table of order p on the device (built once)."""
+    """Reference-element contraction table of order p on the device, built once per order and device by
+    pg_tables_init (basis evaluation + exact quadrature + contraction, all in the library)."""
     dev = _dev(device)
     key = (p, str(dev))
     if key not in _TABLE_CACHE:
-        _TABLE_CACHE[key] = torch.from_numpy(_table_host(p)).to(dev)
+        nexp = lib().pg_nexp(p)
+        tab = torch.empty((nexp, nexp, 12), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().pg_tables_init(p, ptr(tab), stream_ptr()), "pg_tables_init")
+        _TABLE_CACHE[key] = tab
     return _TABLE_CACHE[key]
+
+
+def locate_points(elems: "ElementData", points) -> torch.Tensor:
+    """Containing element of each point (lowest index; -1: outside the mesh) -> int32 [npts] on the device
+    (postprocessing.py:532-539 / preprocessing.py:414-420)."""
+    pts = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(points), dtype=np.float64)).to(elems.device)
+    out = torch.empty((pts.shape[0],), dtype=torch.int32, device=elems.device)
+    check(lib().pg_locate_points(elems.T, ptr(elems.nodes), pts.shape[0], ptr(pts), 1.0e-12, ptr(out), stream_ptr()),
+          "pg_locate_points")
+    return out
+
+
+def interpolate_fields(elems: "ElementData", p: int, code: torch.Tensor, x: torch.Tensor, points, pt_elem, omega: float,
+                       mu: float = MU0, perm: torch.Tensor = None) -> torch.Tensor:
+    """fieldInterpolator (postprocessing.py:479-616) on the device -> [npts, 6] complex128 (E, H)."""
+    pts = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(points), dtype=np.float64)).to(elems.device)
+    out = torch.empty((pts.shape[0], 6), dtype=torch.complex128, device=elems.device)
+    check(lib().pg_interpolate_fields(pts.shape[0], ptr(pts), ptr(pt_elem), p, ptr(elems.nodes), ptr(code),
+                                      ptr(elems.elemsE), ptr(elems.elemsF), elems.nEdges, elems.nFaces, ptr(perm),
+                                      ptr(x), float(omega), float(mu), ptr(out), stream_ptr()), "pg_interpolate_fields")
+    return out
+
+
+def csem_rhs(elems: "ElementData", p: int, code: torch.Tensor, source_elem: int, position, moment, omega: float,
+             b: torch.Tensor, mu: float = MU0, perm: torch.Tensor = None, row_begin: int = 0) -> torch.Tensor:
+    """b += i omega mu (moment . N_j(position)) on the dofs of the source element (solver.py:247-316)."""
+    pos = np.ascontiguousarray(position, dtype=np.float64)
+    mom = np.ascontiguousarray(moment, dtype=np.float64)
+    check(lib().pg_csem_rhs(p, int(source_elem), ptr(pos), ptr(mom), ptr(elems.nodes), ptr(code), ptr(elems.elemsE),
+                            ptr(elems.elemsF), elems.nEdges, elems.nFaces, ptr(perm), int(row_begin), b.numel(),
+                            float(omega), float(mu), ptr(b), stream_ptr()), "pg_csem_rhs")
+    return b
 
 
 class ElementData:
@@ -397,5 +434,6 @@ class CSRMatrix:
 
 __all__ = [
     "ElementData", "AssemblyPlan", "CSRMatrix", "element_table", "element_matrices", "element_systems", "MU0",
+    "locate_points", "interpolate_fields", "csem_rhs",
     "PetgemB200Error",
 ]

@@ -9,10 +9,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import hvfem
 from .common import Print, Timers
 from .parallel import MPIEnvironment, readPetscVector
-from .preprocessing import locate_points, read_receivers
+from .preprocessing import read_receivers
 
 
 def fieldInterpolator(solution_vector, nodes, elemsN, elemsE, edgesN, elemsF, facesE, dof_connectivity, points,
@@ -24,27 +23,29 @@ def fieldInterpolator(solution_vector, nodes, elemsN, elemsE, edgesN, elemsF, fa
     data_model = model.get(mode)
     frequency = data_model.get('source').get('frequency') if mode == 'csem' else data_model.get('frequency')
     omega, mu = frequency * 2. * np.pi, 4. * np.pi * 1e-7
-    Const = 1j * omega * mu
+    import torch
+
+    from .device import ElementData, interpolate_fields, locate_points
+
     x = np.asarray(solution_vector.getArray() if hasattr(solution_vector, 'getArray') else solution_vector)
     points = np.atleast_2d(points)
-    idx = locate_points(nodes, elemsN, points)
+    # receivers are located and the basis evaluated at them on the device (pg_locate_points,
+    # pg_interpolate_fields); x is in the reference dof numbering, like x{i}.dat
+    elemsN = np.asarray(elemsN)
+    el = ElementData.from_mesh(nodes, elemsN, elemsE, edgesN, elemsF, facesE, np.ones((elemsN.shape[0], 2)))
+    idx_dev = locate_points(el, points)
+    idx = idx_dev.cpu().numpy()
     lost = np.nonzero(idx < 0)[0]
     if lost.size:
         Print.master('        The following receivers were not located and will not be taken into account ' + str(lost))
-        points, idx = points[idx >= 0], idx[idx >= 0]
-        if idx.size == 0:
+        points = points[idx >= 0]
+        idx_dev = idx_dev[torch.as_tensor(idx >= 0, device=idx_dev.device)].contiguous()
+        if points.shape[0] == 0:
             Print.master('     No point has been found. Nothing to do. Aborting')
             exit(-1)
-    fields = np.zeros((points.shape[0], 6), dtype=np.complex128)
-    for i, (pt, t) in enumerate(zip(points, idx)):
-        coordEle = nodes[elemsN[t]]
-        jac, ijac = hvfem.computeJacobian(coordEle)
-        eo, fo = hvfem.computeElementOrientation(elemsE[t], elemsN[t], edgesN[elemsE[t]], facesE[elemsF[t]])
-        X = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, pt)
-        basis, curl = hvfem.computeBasisFunctions(eo, fo, jac, ijac, p, X)
-        xe = x[dof_connectivity[t]]
-        fields[i, :3] = basis[:, :, 0] @ xe
-        fields[i, 3:] = (curl[:, :, 0] @ xe) / Const
+    _, code = el.geometry()
+    xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.complex128), device=el.device)
+    fields = interpolate_fields(el, p, code, xd, points, idx_dev, omega, mu).cpu().numpy()
     return fields
 
 

@@ -136,20 +136,22 @@ class Solver():
             moment = src.get('current') * src.get('length')
             field = rot[0] * np.array([moment, 0., 0.]) + rot[1] * np.array([0., moment, 0.]) \
                 + rot[2] * np.array([0., 0., moment])
-            # b and x are replicated on every rank (the reference inserts on rank 0 into a distributed Vec)
+            # b and x are replicated on every rank (the reference inserts on rank 0 into a distributed Vec);
+            # the basis of the source element is evaluated at the dipole position on the device (pg_csem_rhs)
+            from .device import csem_rhs
             sd = self.source_data.getArray().real
             nodesEle = sd[0:4].astype(np.int64)
-            coordEle = sd[4:16].reshape(4, 3)
-            edgesFace = sd[20:32].astype(np.int64).reshape(4, 3)
-            edgesEle = sd[32:38].astype(np.int64)
-            edgesNodesEle = sd[38:50].astype(np.int64).reshape(6, 2)
             dofsSource = sd[50:].astype(np.int64)
-            jacobian, invjacobian = hvfem.computeJacobian(coordEle)
-            eo, fo = hvfem.computeElementOrientation(edgesEle, nodesEle, edgesNodesEle, edgesFace)
-            XiEtaZeta = hvfem.tetrahedronXYZToXiEtaZeta(coordEle, position)
-            basis, _ = hvfem.computeBasisFunctions(eo, fo, jacobian, invjacobian, basis_order, XiEtaZeta)
-            rhs_contribution = np.matmul(field, basis[:, :, 0]) * Const
-            self.b[0].setValues(dofsSource, rhs_contribution, addv=True)
+            # source.dat holds the rows of the source element (preprocessing.py:404-464): find it in the mesh
+            hit = np.nonzero((self.elemsN == nodesEle[None, :]).all(axis=1))[0]
+            if hit.size == 0 or not np.array_equal(self.dofs[hit[0]], dofsSource):
+                Print.master('     source.dat is not consistent with the mesh files')
+                exit(-1)
+            te = int(hit[0])
+            t0, t1 = self.plan.element_range
+            if not (t0 <= te < t1):  # orientation codes exist for this rank's elements only
+                self.elems.geometry((te, te + 1), out=(geo, code))
+            csem_rhs(self.elems, basis_order, code, te, position, field, omega, self.b[0].t, mu)
         elif mode == 'mt':
             # Neumann excitation from the 1-D layered-earth solution on the box sides (solver.py:318-512):
             # host numpy on every rank (b is replicated), like the reference's serial loops

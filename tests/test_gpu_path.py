@@ -587,7 +587,7 @@ def test_gradient_space_kernels(topo, p, order):
         Z = torch.empty((plan.N, k), dtype=torch.complex128, device=dev)
         gs.apply(torch.as_tensor(R, device=dev), torch.as_tensor(dinv, device=dev), Z)
         ref = dinv[:, None] * R + G @ (dg[:, None] * (G.T @ R))
-        assert np.abs(Z.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+        assert np.abs(Z.cpu().numpy() - ref).max() <= 1e-10 * np.abs(ref).max()  # dg itself is matched to 1e-10
     # the operator is complex symmetric: u^T M^-1 v = v^T M^-1 u
     op = krylov.Operator(A, pc="hiptmair")
     u = torch.as_tensor(rng.normal(size=plan.N) + 0j, device=dev)
