@@ -37,6 +37,7 @@ extern "C" {
 #define PG_ENOMEM -12   /* device allocation failed */
 #define PG_ECUDA -5     /* CUDA runtime error; see pg_last_error() */
 #define PG_ERANGE -34   /* a size exceeds what the index types can hold */
+#define PG_ETIMEDOUT -110 /* a peer GPU did not answer (pg_comm_status) */
 
 #define PG_MAX_ORDER 6
 #define PG_SLOTS 11     /* entity slots of a tetrahedron: 6 edges, 4 faces, 1 interior */
@@ -336,6 +337,49 @@ int pg_galerkin_diagonal(int64_t rows, const int32_t *r_rowptr, const int32_t *r
                          double *out, void *stream);
 /* d[i] = 1/d[i] (complex), 0 where d[i] == 0 or mask[i] == 0 (mask u8 [n] or NULL) */
 int pg_masked_reciprocal(int64_t n, const uint8_t *mask, double *d, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * e: the two collectives of a multi-GPU Krylov iteration, over peer memory (NVLink / NVSwitch) instead of
+ * a library: the VecScatter inside MatMult and the MPI_Allreduce inside VecDot / VecNorm of KSP.solve
+ * (solver.py:584-590) on the row-partitioned objects of createParallelMatrix / createParallelVector
+ * (parallel.py:150-203).  One process per GPU; every process maps the buffers of the others (CUDA IPC).
+ * All calls are plain kernel launches with device-resident sequence counters (CUDA-graph capturable);
+ * waits are bounded by the timeout given to pg_comm_create and raise a sticky error (pg_comm_status).
+ *
+ * pg_ipc_*: device memory that other processes of the box can map.  handle_host: PG_IPC_HANDLE_BYTES bytes
+ *   the caller ships to the peers by whatever transport it has (MPI, torch.distributed, a file).
+ * pg_comm_create: ctrl_host[r] = the control block (pg_comm_ctrl_bytes() zeroed bytes from pg_ipc_alloc) of
+ *   rank r as mapped in THIS process (own pointer at [rank]).
+ * pg_comm_allreduce: out[0..k) = sum over ranks of in[0..k) (k complex scalars, k <= PG_COMM_MAX_REDUCE), added
+ *   in rank order on every rank (bit-identical everywhere); out may alias in.
+ * pg_comm_push: halo push on channel `chan`: for every destination rank d and entry e of its segment
+ *   [seg_host[d], seg_host[d+1]):  dst_host[d][(e - seg_host[d])*k + r] = x[send_idx[e]*k + r]  (complex,
+ *   k interleaved right-hand sides), dst_host[d] being a pointer INTO rank d's mapped buffer; then a flag on d.
+ *   Before writing to d it waits for d's acknowledgement of the previous push on the channel.
+ * pg_comm_wait / pg_comm_ack: reader side of a channel, bracketing the kernels that read the pushed entries:
+ *   wait until every rank of from_mask (bit r = rank r sends to me) has pushed; ack tells them the entries
+ *   have been consumed.  Every push on a channel must be matched by one wait + ack on each destination.
+ * --------------------------------------------------------------------------- */
+#define PG_IPC_HANDLE_BYTES 64
+#define PG_COMM_MAX_RANKS 16
+#define PG_COMM_MAX_CHANNELS 64
+#define PG_COMM_MAX_REDUCE 64
+typedef struct pg_comm pg_comm;
+
+int pg_ipc_alloc(int64_t bytes, void **ptr, void *handle_host);
+int pg_ipc_open(const void *handle_host, void **ptr);
+int pg_ipc_close(void *ptr);
+int pg_ipc_free(void *ptr);
+int64_t pg_comm_ctrl_bytes(void);
+int pg_comm_create(int rank, int world, void *const *ctrl_host, double timeout_s, pg_comm **comm);
+void pg_comm_destroy(pg_comm *comm);
+int pg_comm_allreduce(pg_comm *comm, int k, const double *in, double *out, void *stream);
+int pg_comm_push(pg_comm *comm, int chan, int k, const double *x, const int32_t *send_idx, const int64_t *seg_host,
+                 void *const *dst_host, void *stream);
+int pg_comm_wait(pg_comm *comm, int chan, uint32_t from_mask, void *stream);
+int pg_comm_ack(pg_comm *comm, int chan, uint32_t from_mask, void *stream);
+/* PG_OK, or PG_ETIMEDOUT once any wait of this rank has timed out (synchronises the stream) */
+int pg_comm_status(pg_comm *comm, void *stream);
 
 /* CUDA graph of a batch of the calls above (the launches of the Krylov iterations between two host
  * checks of the residual): begin capture on a NON-default stream, issue the calls, end -> executable

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu", "pg_tables.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu", "pg_tables.cu", "pg_comm.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", "pg_basis.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -159,6 +159,18 @@ SIGNATURES = {
     "pg_graph_end": (C.c_int, [_p, C.POINTER(_p)]),
     "pg_graph_launch": (C.c_int, [_p, _p]),
     "pg_graph_destroy": (None, [_p]),
+    "pg_ipc_alloc": (C.c_int, [_i64, C.POINTER(_p), _p]),
+    "pg_ipc_open": (C.c_int, [_p, C.POINTER(_p)]),
+    "pg_ipc_close": (C.c_int, [_p]),
+    "pg_ipc_free": (C.c_int, [_p]),
+    "pg_comm_ctrl_bytes": (_i64, []),
+    "pg_comm_create": (C.c_int, [_i32, _i32, C.POINTER(_p), _d, C.POINTER(_p)]),
+    "pg_comm_destroy": (None, [_p]),
+    "pg_comm_allreduce": (C.c_int, [_p, _i32, _p, _p, _p]),
+    "pg_comm_push": (C.c_int, [_p, _i32, _i32, _p, _p, C.POINTER(_i64), C.POINTER(_p), _p]),
+    "pg_comm_wait": (C.c_int, [_p, _i32, C.c_uint32, _p]),
+    "pg_comm_ack": (C.c_int, [_p, _i32, C.c_uint32, _p]),
+    "pg_comm_status": (C.c_int, [_p, _p]),
     "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
