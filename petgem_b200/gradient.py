@@ -200,15 +200,19 @@ class GradientSpace:
     # ---- multi-GPU: H1 functions reached from the rows of several ranks -------------------------
     def _build_interface(self):
         ctx, dev = self.ctx, self.h1_ids.device
-        dist = ctx.dist
         sizes = torch.zeros((ctx.world,), dtype=torch.int64, device=dev)
         sizes[ctx.rank] = self.nh
-        dist.all_reduce(sizes, group=ctx.group)
+        ctx._sum(sizes)
         smax = int(sizes.max().item())
         mine = torch.full((smax,), -1, dtype=torch.int64, device=dev)
         mine[: self.nh] = self.h1_ids
-        allids = torch.empty((ctx.world * smax,), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allids, mine, group=ctx.group)
+        if ctx._staged:  # gloo: host tensors
+            allh = torch.empty((ctx.world * smax,), dtype=torch.int64)
+            ctx.dist.all_gather_into_tensor(allh, mine.cpu(), group=ctx.group)
+            allids = allh.to(dev)
+        else:
+            allids = torch.empty((ctx.world * smax,), dtype=torch.int64, device=dev)
+            ctx.dist.all_gather_into_tensor(allids, mine, group=ctx.group)
         self._shared = []   # per other rank: positions (in my list) of the H1 functions we both reach
         for r in range(ctx.world):
             if r == ctx.rank:
@@ -222,27 +226,78 @@ class GradientSpace:
             self._shared.append(torch.nonzero(theirs[pos] == self.h1_ids).reshape(-1))
         self._splits = [0 if s is None else int(s.numel()) for s in self._shared]
         self._send_idx = torch.cat([s for s in self._shared if s is not None]) if ctx.world > 1 else None
+        self._xchg = None
+        if ctx.peer is not None:
+            # peer transport: the partial sums are pushed into the neighbours' receive areas (laid out by
+            # source rank) and added by one gather kernel: row i of `acc` lists the received copies of
+            # function i in rank order -> deterministic, and the dg_inv scaling rides along
+            from .peer import PeerExchange
 
-    def sum_over_ranks(self, part: torch.Tensor) -> torch.Tensor:
-        """part [nh, k] (or [nh]): partial sums of this rank -> totals, for the functions shared with
-        other ranks one packed all_to_all and an add per neighbour in rank order (deterministic)."""
+            self._xchg = PeerExchange(ctx.peer, self._send_idx, self._splits, self._splits)
+            total = int(sum(self._splits))
+            rows = self._send_idx  # received copy j (source-rank major, same order as my sends) adds to row rows[j]
+            order = torch.argsort(rows, stable=True)
+            self._acc = (_csr_from_sorted(rows[order], self.nh, dev), order.to(torch.int32).contiguous(),
+                         torch.ones((max(total, 1),), dtype=torch.float64, device=dev))
+            self._recv = {}
+
+    def _recv_area(self, k):
+        if k not in self._recv:
+            from .peer import SymmetricBuffer
+
+            total = int(sum(self._splits))
+            buf = SymmetricBuffer(self.ctx.peer, max(total, 1) * k * 16)
+            self._recv[k] = (buf.view(_C128, max(total, 1) * k), self._xchg.target(buf, [0] * self.ctx.world, k), buf)
+        return self._recv[k]
+
+    def close(self):
+        """Collective: release the peer-mapped receive areas."""
+        if getattr(self, "_xchg", None) is not None:
+            for _, _, buf in self._recv.values():
+                buf.close()
+            self._recv = {}
+
+    def sum_over_ranks(self, part: torch.Tensor, scale: torch.Tensor = None) -> torch.Tensor:
+        """part [nh, k] (or [nh]): partial sums of this rank -> totals (times `scale` [nh] if given).  The
+        functions shared with other ranks travel packed: pushed over peer memory and added in rank order by
+        one kernel (transport "peer"), or one all_to_all and an add per neighbour (transport "nccl")."""
         if self._shared is None:
+            if scale is not None:
+                check(lib().pg_zbscale_rows(self.nh, part.reshape(self.nh, -1).shape[1], ptr(scale), ptr(part),
+                                            ptr(part), stream_ptr()), "pg_zbscale_rows")
             return part
         ctx = self.ctx
         flat = part.reshape(self.nh, -1)
         k = flat.shape[1]
+        if self._xchg is not None:
+            recv, dst, _ = self._recv_area(k)
+            self._xchg.push(flat, k, dst)
+            self._xchg.wait()
+            rp, ci, ones = self._acc
+            if scale is None:
+                scale = self._ones()
+            check(lib().pg_rcsr_apply(self.nh, ptr(rp), ptr(ci), ptr(ones), k, ptr(recv), ptr(scale), ptr(scale),
+                                      ptr(flat), ptr(flat), stream_ptr()), "pg_rcsr_apply")
+            self._xchg.ack()
+            return part
         send = flat[self._send_idx].contiguous()
         recv = torch.empty_like(send)
-        ctx.dist.all_to_all_single(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1),
-                                   output_split_sizes=[2 * k * s for s in self._splits],
-                                   input_split_sizes=[2 * k * s for s in self._splits], group=ctx.group)
+        ctx._a2a(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1),
+                 [2 * k * s for s in self._splits], [2 * k * s for s in self._splits])
         off = 0
         for r, idx in enumerate(self._shared):
             if idx is None or idx.numel() == 0:
                 continue
             flat.index_add_(0, idx, recv[off: off + idx.numel()])
             off += idx.numel()
+        if scale is not None:
+            check(lib().pg_zbscale_rows(self.nh, k, ptr(scale), ptr(flat), ptr(flat), stream_ptr()), "pg_zbscale_rows")
         return part
+
+    def _ones(self):
+        if getattr(self, "_one", None) is None:
+            self._one = torch.ones((max(self.nh, 1),), dtype=_C128, device=self.g_val.device)
+        return self._one
 
     # ---- numeric setup -----------------------------------------------------------------------------
     def setup(self, A_local):
@@ -277,8 +332,7 @@ class GradientSpace:
         else:
             check(L.pg_rcsr_apply(self.nh, ptr(self.gt_rowptr), ptr(self.gt_col), ptr(self.gt_val), k, ptr(R),
                                   None, None, None, ptr(y), stream_ptr()), "pg_rcsr_apply")
-            self.sum_over_ranks(y)
-            check(L.pg_zbscale_rows(self.nh, k, ptr(self.dg_inv), ptr(y), ptr(y), stream_ptr()), "pg_zbscale_rows")
+            self.sum_over_ranks(y, self.dg_inv)
         check(L.pg_rcsr_apply(self.n_own, ptr(self.g_rowptr), ptr(self.g_col), ptr(self.g_val), k, ptr(y), None,
                               ptr(dinv), ptr(R), ptr(Z), stream_ptr()), "pg_rcsr_apply")
         return Z

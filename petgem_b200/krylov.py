@@ -27,9 +27,14 @@ _C128 = torch.complex128
 
 
 class DistContext:
-    """Row-block ownership across ranks (PETSc-style contiguous blocks, entity aligned)."""
+    """Row-block ownership across ranks (PETSc-style contiguous blocks, entity aligned).
 
-    def __init__(self, row_begins, N, group=None):
+    transport: how the two per-iteration collectives travel.  "peer" (default on CUDA): kernels over
+    IPC-mapped peer memory (peer.py / csrc/pg_comm.cu: halo push + flag wait, one-kernel all-reduce, CUDA
+    graph capturable); "nccl": torch.distributed collectives (all_to_all_single + all_reduce), kept as the
+    A/B baseline and for the CPU (gloo) tests of the host logic.  PG_TRANSPORT overrides the default."""
+
+    def __init__(self, row_begins, N, group=None, transport=None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -40,6 +45,40 @@ class DistContext:
         self.N = int(N)
         self.sizes = [self.row_begins[i + 1] - self.row_begins[i] for i in range(self.world)]
         self.max_rows = max(self.sizes)
+        self._staged = dist.get_backend(group) == "gloo"  # gloo moves host tensors only
+        transport = transport or os.environ.get("PG_TRANSPORT", "auto")
+        if transport == "auto":
+            transport = "peer" if (torch.cuda.is_available() and self.world > 1) else "nccl"
+        if transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        self.transport = transport
+        self.peer = None
+        if transport == "peer" and self.world > 1:
+            from .peer import PeerComm
+
+            self.peer = PeerComm(dist, group)
+
+    # set-up collectives (torch.distributed; staged through the host when the backend is gloo)
+    def _a2a(self, out, inp, out_splits=None, in_splits=None):
+        if self._staged and inp.is_cuda:
+            o = torch.empty(out.shape, dtype=out.dtype)
+            self.dist.all_to_all_single(o, inp.cpu(), output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                        group=self.group)
+            out.copy_(o)
+        else:
+            self.dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                        group=self.group)
+        return out
+
+    def _sum(self, t, op=None):
+        op = op or self.dist.ReduceOp.SUM
+        if self._staged and t.is_cuda:
+            h = t.cpu()
+            self.dist.all_reduce(h, op=op, group=self.group)
+            t.copy_(h)
+        else:
+            self.dist.all_reduce(t, op=op, group=self.group)
+        return t
 
     def remap_columns(self, colidx: torch.Tensor) -> torch.Tensor:
         """Global column -> index in the padded all-gather buffer [world, max_rows]."""
@@ -55,14 +94,25 @@ class DistContext:
         return full
 
     def allreduce(self, t: torch.Tensor) -> None:
-        self.dist.all_reduce(torch.view_as_real(t), op=self.dist.ReduceOp.SUM, group=self.group)
+        """Sum of a few complex scalars over the ranks (the VecDot / VecNorm all-reduce)."""
+        if self.peer is not None and t.is_cuda and t.dtype == _C128 and t.numel() <= 64 and t.is_contiguous():
+            self.peer.allreduce(t)
+        else:
+            self._sum(torch.view_as_real(t))
+
+    def agree(self, flag: bool) -> bool:
+        """True on every rank if `flag` is true on any (decisions taken from per-rank wall clocks)."""
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64,
+                         device="cuda" if torch.cuda.is_available() else "cpu")
+        self._sum(t, self.dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
 
     def build_halo(self, colidx: torch.Tensor):
         """Neighbour halo instead of the full all-gather (what PETSc's VecScatter does for MatMult).
 
         Returns (colidx_local, send_idx, send_splits, recv_splits): columns remapped into
         [own rows | received halo entries], the local row indices this rank must send (grouped by
-        destination rank) and the per-rank counts for all_to_all_single.  With the element-major
+        destination rank) and the per-rank counts of the exchange.  With the element-major
         internal numbering the halo is the thin interface between spatial slabs."""
         dev = colidx.device
         lo, hi = self.row_begins[self.rank], self.row_begins[self.rank + 1]
@@ -73,11 +123,10 @@ class DistContext:
         owner = torch.bucketize(ext, starts, right=True) - 1
         recv_counts = torch.bincount(owner, minlength=self.world)
         send_counts = torch.empty_like(recv_counts)
-        self.dist.all_to_all_single(send_counts, recv_counts, group=self.group)
+        self._a2a(send_counts, recv_counts)
         recv_splits, send_splits = recv_counts.tolist(), send_counts.tolist()
         wanted = torch.empty((int(sum(send_splits)),), dtype=torch.int64, device=dev)
-        self.dist.all_to_all_single(wanted, ext, output_split_sizes=send_splits, input_split_sizes=recv_splits,
-                                    group=self.group)
+        self._a2a(wanted, ext, send_splits, recv_splits)
         send_idx = wanted - lo  # rows of mine the others asked for, grouped by destination
         n = hi - lo
         self._halo_ext, self._halo_lo, self._halo_hi = ext, lo, hi
@@ -92,7 +141,7 @@ class DistContext:
         return torch.where(outside, n + torch.searchsorted(self._halo_ext, c), c - self._halo_lo).to(torch.int32)
 
     def exchange(self, x_local, send_idx, send_splits, recv_splits, sendbuf, xbuf):
-        """xbuf = [x_local | halo]: pack, all_to_all over NCCL, unpack in place."""
+        """xbuf = [x_local | halo]: pack, all_to_all over NCCL, unpack in place (transport "nccl")."""
         n = x_local.numel()
         xbuf[:n].copy_(x_local)
         torch.index_select(x_local, 0, send_idx, out=sendbuf)
@@ -135,6 +184,7 @@ class Operator:
             if halo == "auto" and ctx is not None and ctx.world > 1:
                 halo = "p2p"  # the gradient space is built in the [own | halo] numbering of the neighbour halo
         self.mode = "single"
+        self.xchg = None  # peer-memory halo (transport "peer")
         if ctx is not None and ctx.world > 1:
             # x exchange before the SpMV: neighbour halo (packed all_to_all) when the off-block column
             # set is small -- the case with the element-major numbering -- else all-gather of x
@@ -143,12 +193,18 @@ class Operator:
                 col_l, self.send_idx, self.send_splits, self.recv_splits = ctx.build_halo(A.colidx)
                 next_ = int(sum(self.recv_splits))
                 frac = torch.tensor([next_ / max(self.n, 1)], dtype=torch.float64, device=dev)
-                ctx.dist.all_reduce(frac, op=ctx.dist.ReduceOp.MAX, group=ctx.group)
+                ctx._sum(frac, ctx.dist.ReduceOp.MAX)
                 self.mode = "p2p" if (halo == "p2p" or frac.item() < 0.5) else "allgather"
                 if self.mode == "p2p":
                     self.halo_entries = next_
-                    self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
-                    self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
+                    if ctx.peer is not None:
+                        from .peer import PeerExchange
+
+                        self.xchg = PeerExchange(ctx.peer, self.send_idx, self.send_splits, self.recv_splits)
+                        self._halo_vectors = {}
+                    else:
+                        self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
+                        self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
                     pref = getattr(A, "plan_ref", None)
                     cs = ctx.remap_halo(pref.column_starts()) if pref is not None else None
                     self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=pref,
@@ -171,8 +227,52 @@ class Operator:
             self.grad.setup(self.A_halo if dist_run else A)
         self.spmv_calls = 0
 
+    # -- peer transport: vectors that live in peer-mapped memory with their halo behind them ----------
+    def halo_vector(self, k=None, tag="krylov"):
+        """[n + halo] (k None) or [n + halo, k] complex vector in peer-mapped memory: the first n rows are
+        this rank's entries, the tail is filled by the neighbours (pg_comm_push).  A Krylov driver keeps the
+        vector it multiplies with A here (`[:n]` of it), so MatMult needs no copy of x.  Collective."""
+        key = (k, tag)
+        hv = self._halo_vectors.get(key)
+        if hv is None:
+            from .peer import SymmetricBuffer
+
+            kk = 1 if k is None else int(k)
+            buf = SymmetricBuffer(self.ctx.peer, (self.n + self.halo_entries) * kk * 16)
+            t = buf.view(_C128, (self.n + self.halo_entries) * kk)
+            t = t if k is None else t.view(self.n + self.halo_entries, kk)
+            dst = self.xchg.target(buf, [sz * kk * 16 for sz in self.ctx.sizes], kk)
+            hv = self._halo_vectors[key] = (t, dst, buf, kk)
+            self._by_ptr = {v[0].data_ptr(): v for v in self._halo_vectors.values()}
+        return hv[0]
+
+    def _peer_product(self, x, k, mult):
+        hv = self._by_ptr.get(x.data_ptr()) if self._halo_vectors else None
+        if hv is None or hv[3] != k:
+            full = self.halo_vector(None if x.dim() == 1 else k, tag="scratch")  # not resident: one copy of x
+            full[: self.n].copy_(x)
+            hv = self._by_ptr[full.data_ptr()]
+        full = hv[0]
+        if full.dim() != x.dim():  # an [n, 1] block and a vector share the layout
+            full = full.reshape(-1) if x.dim() == 1 else full.reshape(-1, 1)
+        self.xchg.push(full, k, hv[1])
+        self.xchg.wait()
+        mult(full)
+        self.xchg.ack()
+
+    def close(self):
+        """Collective: release the peer-mapped vectors."""
+        if self.xchg is not None:
+            for _, _, buf, _ in self._halo_vectors.values():
+                buf.close()
+            self._halo_vectors, self._by_ptr = {}, {}
+        if self.grad is not None:
+            self.grad.close()
+
     def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
-        if self.mode == "p2p":
+        if self.mode == "p2p" and self.xchg is not None:
+            self._peer_product(x, 1, lambda full: self.A_halo.mult(full, y, row_scale))
+        elif self.mode == "p2p":
             self.ctx.exchange(x, self.send_idx, self.send_splits, self.recv_splits, self.sendbuf, self.xbuf)
             self.A_halo.mult(self.xbuf, y, row_scale)
         elif self.mode == "allgather":
@@ -189,7 +289,9 @@ class Operator:
         if k == 1:  # an [n, 1] block is a vector: every halo mode applies
             self.matvec(X.reshape(-1), Y.reshape(-1), row_scale)
             return Y
-        if self.mode == "p2p":
+        if self.mode == "p2p" and self.xchg is not None:
+            self._peer_product(X, k, lambda full: self.A_halo.mult_multi(full, Y, row_scale))
+        elif self.mode == "p2p":
             if getattr(self, "_mm", None) is None or self._mm[0] != k:
                 dev = X.device
                 self._mm = (k, torch.zeros((int(sum(self.send_splits)), k), dtype=_C128, device=dev),
@@ -570,6 +672,15 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
     work = torch.empty((L.pg_reduce_workspace_bytes(2 * k) // 16,), dtype=_C128, device=dev)
     Z_ = lambda: torch.zeros((n, k), dtype=_C128, device=dev)  # noqa: E731
     X, R, Z, P, Q = Z_(), B.contiguous().clone(), Z_(), Z_(), Z_()
+    if op.xchg is not None:
+        # peer transport: the vector that is multiplied with A every iteration (COCR: the preconditioned
+        # residual, COCG: the direction) lives in peer-mapped memory in front of its halo
+        hv = op.halo_vector(k)[:n]
+        hv.zero_()
+        if method == "cocr":
+            Z = hv
+        else:
+            P = hv
     rho = [torch.zeros((k,), dtype=_C128, device=dev) for _ in range(2)]
     pq = torch.zeros((k,), dtype=_C128, device=dev)
     alpha2 = torch.zeros((2 * k,), dtype=_C128, device=dev)
@@ -681,7 +792,8 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
     gexec = _C.c_void_p()
     side = None
     first = False
-    if ctx is None and check_every > 0 and os.environ.get("PG_CUDA_GRAPH", "1") == "1" and maxit >= 2 * check_every:
+    graphable = ctx is None or (ctx.peer is not None and op.mode == "p2p")  # every collective is a kernel
+    if graphable and check_every > 0 and os.environ.get("PG_CUDA_GRAPH", "1") == "1" and maxit >= 2 * check_every:
         main_stream = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(main_stream)
@@ -708,6 +820,8 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
                     iterations(count)
                 it += count
             res2 = out2[k:].real.cpu().numpy()  # the host sync of this batch
+            if ctx is not None and ctx.peer is not None:
+                ctx.peer.status()  # a peer that stopped answering raises here instead of hanging the box
             if not np.isfinite(res2).all():
                 return MultiSolveResult(X, it, hist, np.zeros(k, dtype=bool), "breakdown")
             res = np.sqrt(res2)
@@ -726,7 +840,8 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
                 out = MultiSolveResult(X, it, hist, done, "rtol")
                 out.true_residuals = true_hist
                 return out
-            if max_seconds is not None and _time.time() - t_start > max_seconds:
+            if max_seconds is not None and (_time.time() - t_start > max_seconds if ctx is None else
+                                            ctx.agree(_time.time() - t_start > max_seconds)):
                 out = MultiSolveResult(X, it, hist, done, "time limit")
                 out.true_residuals = true_hist
                 return out
