@@ -854,7 +854,11 @@ def main():
     A = CSRMatrix(rowptr, colidx, vals, plan.N, plan.row_begin, plan=plan)  # p=2: entity-blocked MatMult
     ctx = krylov.DistContext(row_begins, plan.N) if world > 1 else None
     op = krylov.Operator(A, pc="jacobi", ctx=ctx)
-    xg = torch.ones((plan.local_rows,), dtype=torch.complex128, device=dev)
+    if op.xchg is not None:  # peer transport: x lives in front of its halo, as in the Krylov drivers
+        xg = op.halo_vector(None, tag="bench")[: plan.local_rows]
+        xg.fill_(1.0)
+    else:
+        xg = torch.ones((plan.local_rows,), dtype=torch.complex128, device=dev)
     yg = torch.empty_like(xg)
     for _ in range(3):
         op.matvec(xg, yg)
@@ -873,10 +877,15 @@ def main():
     spmv_bytes = 20.0 * nnz_total + 40.0 * rows_total
     spmv = {"ms": spmv_ms, "gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
             "frac_of_peak": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / (peak * world), "nnz": nnz_total, "rows": rows_total,
-            "includes_halo_exchange": world > 1}
+            "includes_halo_exchange": world > 1,
+            "transport": (ctx.transport if ctx is not None else None), "halo_mode": op.mode}
     # four right-hand sides per pass over the matrix (sources sharing A): bytes = 20 nnz + 4 * 40 rows
     if op.mode in ("single", "p2p"):
-        Xm = torch.ones((plan.local_rows, 4), dtype=torch.complex128, device=dev)
+        if op.xchg is not None:
+            Xm = op.halo_vector(4, tag="bench")[: plan.local_rows]
+            Xm.fill_(1.0)
+        else:
+            Xm = torch.ones((plan.local_rows, 4), dtype=torch.complex128, device=dev)
         Ym = torch.empty_like(Xm)
         for _ in range(3):
             op.matmat(Xm, Ym)
@@ -1041,6 +1050,8 @@ def main():
     parity = None
     if world > 1 and not args.no_solve:
         parity = parity_block(el, tab, p, args.order, dev, rank, world, dist, sums)
+        if parity is not None:
+            parity["transport"] = ctx.transport  # "peer": pg_comm kernels over NVLink; "nccl": torch.distributed
 
     # ---- CPU baselines (rank 0, N=1 only) --------------------------------------------------------------
     cpu = None

@@ -282,15 +282,24 @@ int pg_zbdiv(int k, const double *a, const double *b, double *out, void *stream)
 int pg_cocg_step(int64_t n, int k, const double *alpha2, const double *P, const double *Q, const double *dinv,
                  double *X, double *R, double *Z, double *out, void *work, void *stream);
 
-/* The whole solve as one call on one GPU (full matrix): COCG (method 0, -ksp_type cg -ksp_cg_type
- * symmetric) or COCR (method 1, -ksp_type cr) with optional Jacobi preconditioning, zero initial guess,
- * convergence on ||M^-1 r|| <= rtol ||M^-1 b|| checked every check_every iterations (solver.py:584-590).
- * work = pg_krylov_workspace_bytes(n) bytes of device memory; iterations and rel_residual are host
- * outputs; returns PG_OK also when maxit is reached (compare rel_residual with rtol). */
-int64_t pg_krylov_workspace_bytes(int64_t n);
+/* The whole solve as one call on one GPU (full matrix), zero initial guess, optional Jacobi preconditioning,
+ * convergence on ||M^-1 r|| <= rtol ||M^-1 b|| (KSP defaults with left preconditioning; solver.py:584-590):
+ *   PG_KSP_COCG  -ksp_type cg -ksp_cg_type symmetric   (A is complex symmetric)
+ *   PG_KSP_COCR  -ksp_type cr (conjugate-orthogonal conjugate residuals)
+ *   PG_KSP_BCGS  -ksp_type bcgs
+ *   PG_KSP_GMRES -ksp_type gmres, restart = -ksp_gmres_restart (PETSc default 30), classical Gram-Schmidt
+ * COCG / COCR check the residual every check_every iterations (coefficients stay on the device); BiCGStab
+ * and GMRES read their scalars every iteration.  work = pg_krylov_workspace_bytes(n, method, restart) bytes
+ * of device memory; iterations and rel_residual are host outputs; returns PG_OK also when maxit is reached
+ * (compare rel_residual with rtol). */
+#define PG_KSP_COCG 0
+#define PG_KSP_COCR 1
+#define PG_KSP_BCGS 2
+#define PG_KSP_GMRES 3
+int64_t pg_krylov_workspace_bytes(int64_t n, int method, int restart);
 int pg_krylov_solve(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *b,
-                    double *x, int method, int jacobi, double rtol, int maxit, int check_every, void *work,
-                    int *iterations, double *rel_residual, void *stream);
+                    double *x, int method, int restart, int jacobi, double rtol, int maxit, int check_every,
+                    void *work, int *iterations, double *rel_residual, void *stream);
 
 /* ---------------------------------------------------------------------------
  * f1: the callers on either side of the solve, on the device.

@@ -143,8 +143,8 @@ SIGNATURES = {
     "pg_cocr_direction": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
     "pg_zbnrm2sq": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "pg_zbdiv": (C.c_int, [_i32, _p, _p, _p, _p]),
-    "pg_krylov_workspace_bytes": (_i64, [_i64]),
-    "pg_krylov_solve": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i32, _i32, _d, _i32, _i32, _p, C.POINTER(C.c_int),
+    "pg_krylov_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "pg_krylov_solve": (C.c_int, [_i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _d, _i32, _i32, _p, C.POINTER(C.c_int),
                                   C.POINTER(C.c_double), _p]),
     "pg_table_size": (_i64, [_i32]),
     "pg_tables_init": (C.c_int, [_i32, _p, _p]),

@@ -484,10 +484,11 @@ def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
         from petgem_b200._lib import check, lib, ptr, stream_ptr
         L = lib()
         n = A.rows
-        work = torch.empty((L.pg_krylov_workspace_bytes(n) // 16,), dtype=torch.complex128, device=bd.device)
+        method = 0 if ksp == "cg" else 1
+        work = torch.empty((L.pg_krylov_workspace_bytes(n, method, 0) // 16,), dtype=torch.complex128, device=bd.device)
         xc = torch.empty_like(bd)
         its, rel = C.c_int(0), C.c_double(0.0)
-        check(L.pg_krylov_solve(n, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), ptr(bd), ptr(xc), 0 if ksp == "cg" else 1,
+        check(L.pg_krylov_solve(n, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), ptr(bd), ptr(xc), method, 0,
                                 1, 1e-8, 20000, 10, ptr(work), C.byref(its), C.byref(rel), stream_ptr()),
               "pg_krylov_solve")
         assert rel.value <= 1e-8 and abs(its.value - r8.iterations) <= 10, (ksp, its.value, r8.iterations, rel.value)
@@ -509,6 +510,24 @@ def test_krylov_receiver_fields_match_direct_solve(topo, oracle):
     Eb = oracle.field_interpolator(resb.x.cpu().numpy(), topo["nodes"], topo["elemsN"], topo["elemsE"],
                                    topo["edgesNodes"], topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
     assert np.abs(Eb[:, :3] - Ed[:, :3]).max() <= 1e-6 * scale
+    # GMRES(30) and BiCGStab as ONE C-ABI call each (pg_krylov_solve, PG_KSP_GMRES / PG_KSP_BCGS): the
+    # iteration counts of the Python drivers (GMRES: the same algorithm step by step) and the same fields
+    for method, restart, rtol, pyres in ((3, 30, 1e-8, res8), (2, 0, 1e-10, resb)):
+        work = torch.empty((L.pg_krylov_workspace_bytes(n, method, restart) // 16,), dtype=torch.complex128,
+                           device=bd.device)
+        xc = torch.empty_like(bd)
+        its, rel = C.c_int(0), C.c_double(0.0)
+        check(L.pg_krylov_solve(n, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), ptr(bd), ptr(xc), method, restart,
+                                1, rtol, 20000, 10, ptr(work), C.byref(its), C.byref(rel), stream_ptr()),
+              "pg_krylov_solve")
+        assert rel.value <= rtol, (method, its.value, rel.value)
+        if method == 3:
+            assert abs(its.value - pyres.iterations) <= max(3, pyres.iterations // 50), (its.value, pyres.iterations)
+        else:
+            assert 0.5 * pyres.iterations <= its.value <= 2.0 * pyres.iterations, (its.value, pyres.iterations)
+        Ex = oracle.field_interpolator(xc.cpu().numpy(), topo["nodes"], topo["elemsN"], topo["elemsE"],
+                                       topo["edgesNodes"], topo["elemsF"], topo["facesE"], dofs, rec, p, omega, mu)
+        assert np.abs(Ex[:, :3] - Ed[:, :3]).max() <= (1e-6 if method == 2 else 1e-4) * scale
 
 
 @pytest.mark.parametrize("p", [2, 3])
