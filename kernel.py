@@ -39,6 +39,7 @@ if __name__ == '__main__':
 
     par_env = MPIEnvironment()
     input_setup = InputParameters(args[-1], par_env)   # sys.argv[3] in the reference (kernel.py:35)
+    input_setup.petsc_options = options  # the results file records -ksp_type (postprocessing.py:381-383)
     Timers(input_setup.output['directory'])
     Print.header()
     Print.master(' ')

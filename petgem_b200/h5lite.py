@@ -1,0 +1,258 @@
+"""Minimal HDF5 writer (and reader of what it writes) for the results file of ``Postprocessing.run``.
+
+The reference writes its results with h5py (petgem/postprocessing.py:341-461): groups ``machine`` and ``model``
+holding scalar provenance datasets and the receiver responses.  h5py is not a dependency of this package, so
+the small subset of the HDF5 file format needed for that schema is produced here directly (HDF5 File Format
+Specification v3: version-2 superblock, version-2 object headers with their lookup3 checksums, compact
+new-style groups, contiguous datasets).  Supported values: python/numpy scalars and arrays of float64, int64,
+complex128 (the compound {r, i} h5py uses), bool (h5py's FALSE/TRUE enum) and strings (fixed-length UTF-8).
+``read`` parses the same subset back into nested dicts (used by the tests).
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+_M = 0xFFFFFFFF
+
+
+def _rot(x, k):
+    return ((x << k) | (x >> (32 - k))) & _M
+
+
+def lookup3(data: bytes, initval: int = 0) -> int:
+    """Bob Jenkins' lookup3 hashlittle, the checksum of HDF5 metadata (H5_checksum_lookup3)."""
+    length = len(data)
+    a = b = c = (0xDEADBEEF + length + initval) & _M
+    i = 0
+    while length > 12:
+        a = (a + int.from_bytes(data[i:i + 4], "little")) & _M
+        b = (b + int.from_bytes(data[i + 4:i + 8], "little")) & _M
+        c = (c + int.from_bytes(data[i + 8:i + 12], "little")) & _M
+        a = (a - c) & _M; a ^= _rot(c, 4); c = (c + b) & _M   # noqa: E702
+        b = (b - a) & _M; b ^= _rot(a, 6); a = (a + c) & _M   # noqa: E702
+        c = (c - b) & _M; c ^= _rot(b, 8); b = (b + a) & _M   # noqa: E702
+        a = (a - c) & _M; a ^= _rot(c, 16); c = (c + b) & _M  # noqa: E702
+        b = (b - a) & _M; b ^= _rot(a, 19); a = (a + c) & _M  # noqa: E702
+        c = (c - b) & _M; c ^= _rot(b, 4); b = (b + a) & _M   # noqa: E702
+        i += 12
+        length -= 12
+    if length == 0:
+        return c
+    tail = data[i:] + b"\0" * (12 - length)
+    a = (a + int.from_bytes(tail[0:4], "little")) & _M
+    b = (b + int.from_bytes(tail[4:8], "little")) & _M
+    c = (c + int.from_bytes(tail[8:12], "little")) & _M
+    c ^= b; c = (c - _rot(b, 14)) & _M  # noqa: E702
+    a ^= c; a = (a - _rot(c, 11)) & _M  # noqa: E702
+    b ^= a; b = (b - _rot(a, 25)) & _M  # noqa: E702
+    c ^= b; c = (c - _rot(b, 16)) & _M  # noqa: E702
+    a ^= c; a = (a - _rot(c, 4)) & _M   # noqa: E702
+    b ^= a; b = (b - _rot(a, 14)) & _M  # noqa: E702
+    c ^= b; c = (c - _rot(b, 24)) & _M  # noqa: E702
+    return c
+
+
+# ---- datatype messages -------------------------------------------------------------------------
+def _dt_float64():
+    return struct.pack("<BBBBI", 0x11, 0x20, 0x3F, 0x00, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+
+
+def _dt_int(size, signed=True):
+    return struct.pack("<BBBBI", 0x10, 0x08 if signed else 0x00, 0, 0, size) + struct.pack("<HH", 0, 8 * size)
+
+
+def _dt_string(n):
+    return struct.pack("<BBBBI", 0x13, 0x11, 0, 0, n)  # null-padded, UTF-8
+
+
+def _dt_complex128():
+    body = b"r\0" + struct.pack("<B", 0) + _dt_float64() + b"i\0" + struct.pack("<B", 8) + _dt_float64()
+    return struct.pack("<BBBBI", 0x36, 2, 0, 0, 16) + body  # compound, version 3, two members
+
+
+def _dt_bool():
+    base = _dt_int(1)
+    return struct.pack("<BBBBI", 0x38, 2, 0, 0, 1) + base + b"FALSE\0TRUE\0" + b"\x00\x01"  # enum, version 3
+
+
+def _encode(value):
+    """python / numpy value -> (datatype message, shape, raw little-endian bytes)."""
+    if isinstance(value, (bytes, str)):
+        raw = value.encode("utf-8") if isinstance(value, str) else value
+        raw = raw or b"\0"
+        return _dt_string(len(raw)), (), raw
+    a = np.asarray(value)
+    if a.dtype.kind in ("U", "S", "O"):
+        if a.ndim == 0:
+            return _encode(str(a.item()))
+        items = [str(v).encode("utf-8") for v in a.reshape(-1)]
+        n = max(1, max(len(v) for v in items))
+        return _dt_string(n), a.shape, b"".join(v.ljust(n, b"\0") for v in items)
+    if a.dtype.kind == "b":
+        return _dt_bool(), a.shape, np.ascontiguousarray(a, dtype=np.int8).tobytes()
+    if a.dtype.kind in ("i", "u"):
+        return _dt_int(8), a.shape, np.ascontiguousarray(a, dtype="<i8").tobytes()
+    if a.dtype.kind == "f":
+        return _dt_float64(), a.shape, np.ascontiguousarray(a, dtype="<f8").tobytes()
+    if a.dtype.kind == "c":
+        return _dt_complex128(), a.shape, np.ascontiguousarray(a, dtype="<c16").tobytes()
+    raise TypeError("h5lite: unsupported value of dtype %s" % a.dtype)
+
+
+def _message(mtype, data, flags=0):
+    return struct.pack("<BHB", mtype, len(data), flags) + data
+
+
+def _object_header(messages):
+    body = b"".join(messages)
+    head = b"OHDR" + struct.pack("<BB", 2, 0x02) + struct.pack("<I", len(body))  # chunk-0 size field: 4 bytes
+    blob = head + body
+    return blob + struct.pack("<I", lookup3(blob))
+
+
+class _Writer:
+    def __init__(self):
+        self.buf = bytearray(b"\0" * 48)  # superblock, filled in at the end
+
+    def _align(self, n=8):
+        self.buf.extend(b"\0" * (-len(self.buf) % n))
+
+    def dataset(self, value):
+        dt, shape, raw = _encode(value)
+        self._align()
+        data_addr = len(self.buf)
+        self.buf.extend(raw)
+        if shape == ():
+            space = struct.pack("<BBBB", 2, 0, 0, 0)
+        else:
+            space = struct.pack("<BBBB", 2, len(shape), 0, 1) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+        msgs = [_message(0x01, space), _message(0x03, dt, flags=0x01), _message(0x05, struct.pack("<BB", 3, 0x09)),
+                _message(0x08, struct.pack("<BBQQ", 3, 1, data_addr if raw else _UNDEF, len(raw)))]
+        self._align()
+        addr = len(self.buf)
+        self.buf.extend(_object_header(msgs))
+        return addr
+
+    def group(self, tree):
+        links = []
+        for name, value in tree.items():
+            child = self.group(value) if isinstance(value, dict) else self.dataset(value)
+            nm = str(name).encode("utf-8")
+            if len(nm) > 255:
+                raise ValueError("h5lite: link name longer than 255 bytes")
+            links.append(_message(0x06, struct.pack("<BBBB", 1, 0x10, 1, len(nm)) + nm + struct.pack("<Q", child)))
+        msgs = [_message(0x02, struct.pack("<BBQQ", 0, 0, _UNDEF, _UNDEF)), _message(0x0A, struct.pack("<BB", 0, 0))]
+        self._align()
+        addr = len(self.buf)
+        self.buf.extend(_object_header(msgs + links))
+        return addr
+
+    def finish(self, root):
+        self._align()
+        sb = _SIG + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, _UNDEF, len(self.buf), root)
+        self.buf[:48] = sb + struct.pack("<I", lookup3(sb))
+        return bytes(self.buf)
+
+
+def write(path, tree):
+    """tree: nested dict; a dict is a group, anything else a dataset (scalar or array)."""
+    w = _Writer()
+    blob = w.finish(w.group(tree))
+    with open(path, "wb") as fh:
+        fh.write(blob)
+
+
+# ---- reader of the same subset -------------------------------------------------------------------
+def _parse_dtype(b, o):
+    cls, ver = b[o] & 0x0F, b[o] >> 4
+    bits0, bits1 = b[o + 1], b[o + 2]
+    size = struct.unpack_from("<I", b, o + 4)[0]
+    o += 8
+    if cls == 0:
+        return ("int", size), o + 4
+    if cls == 1:
+        return ("float", size), o + 12
+    if cls == 3:
+        return ("str", size), o
+    if cls == 6 and ver == 3:
+        members = []
+        for _ in range(bits0 | (bits1 << 8)):
+            e = b.index(b"\0", o)
+            name = b[o:e].decode()
+            nb = 1 if size < 256 else 2 if size < 65536 else 4
+            off = int.from_bytes(b[e + 1:e + 1 + nb], "little")
+            mt, o = _parse_dtype(b, e + 1 + nb)
+            members.append((name, off, mt))
+        return ("compound", size, members), o
+    if cls == 8 and ver == 3:
+        base, o = _parse_dtype(b, o)
+        names = []
+        for _ in range(bits0 | (bits1 << 8)):
+            e = b.index(b"\0", o)
+            names.append(b[o:e].decode())
+            o = e + 1
+        return ("enum", size, names), o + len(names) * base[1]
+    raise ValueError("h5lite.read: datatype class %d version %d" % (cls, ver))
+
+
+def _read_object(b, addr):
+    if b[addr:addr + 4] != b"OHDR" or b[addr + 4] != 2:
+        raise ValueError("h5lite.read: not a version-2 object header at %d" % addr)
+    flags = b[addr + 5]
+    o = addr + 6
+    nsz = 1 << (flags & 3)
+    size = int.from_bytes(b[o:o + nsz], "little")
+    o += nsz
+    end = o + size
+    if struct.unpack_from("<I", b, end)[0] != lookup3(bytes(b[addr:end])):
+        raise ValueError("h5lite.read: object header checksum mismatch at %d" % addr)
+    links, dt, shape, layout = {}, None, None, None
+    is_group = False
+    while o < end:
+        mtype, msize, _ = struct.unpack_from("<BHB", b, o)
+        d = o + 4
+        if mtype == 0x02:
+            is_group = True
+        elif mtype == 0x06:
+            lf = b[d + 1]
+            q = d + 2 + (1 if lf & 0x08 else 0) + (8 if lf & 0x04 else 0) + (1 if lf & 0x10 else 0)
+            ln = b[q]
+            links[b[q + 1:q + 1 + ln].decode()] = struct.unpack_from("<Q", b, q + 1 + ln)[0]
+        elif mtype == 0x01:
+            rank = b[d + 1]
+            shape = tuple(struct.unpack_from("<Q", b, d + 4 + 8 * i)[0] for i in range(rank))
+        elif mtype == 0x03:
+            dt, _ = _parse_dtype(b, d)
+        elif mtype == 0x08:
+            layout = struct.unpack_from("<QQ", b, d + 2)
+        o = d + msize
+    if is_group:
+        return {k: _read_object(b, a) for k, a in links.items()}
+    raw = bytes(b[layout[0]:layout[0] + layout[1]]) if layout[1] else b""
+    kind = dt[0]
+    if kind == "str":
+        n = dt[1]
+        vals = [raw[i:i + n].rstrip(b"\0").decode() for i in range(0, len(raw), n)]
+        return vals[0] if shape == () else np.array(vals).reshape(shape)
+    np_dt = {"float": "<f8", "int": "<i%d" % dt[1], "compound": "<c16", "enum": "|i1"}[kind]
+    a = np.frombuffer(raw, dtype=np_dt).reshape(shape)
+    if kind == "enum":
+        a = a.astype(bool)
+    return a[()] if shape == () else a.copy()
+
+
+def read(path):
+    """Nested dicts of what `write` produced (checks the superblock and object-header checksums)."""
+    b = open(path, "rb").read()
+    if b[:8] != _SIG or b[8] != 2:
+        raise ValueError("h5lite.read: not an HDF5 file with a version-2 superblock")
+    if struct.unpack_from("<I", b, 44)[0] != lookup3(b[:44]):
+        raise ValueError("h5lite.read: superblock checksum mismatch")
+    eof, root = struct.unpack_from("<QQ", b, 28)
+    if eof != len(b):
+        raise ValueError("h5lite.read: end-of-file address %d != file size %d" % (eof, len(b)))
+    return _read_object(b, root)

@@ -2,8 +2,12 @@
 
 ``fieldInterpolator`` follows postprocessing.py:479-616 (locate receivers, evaluate the basis at
 the receiver, E = sum_j x_j N_j, H = sum_j x_j curl N_j / (i omega mu)), vectorised with the
-product's basis tables; output is ``<directory>/fields.npz``; the scratch files are removed afterwards
-like the reference does (postprocessing.py:463-472) unless the parameter file says ``remove_scratch: False``.
+product's basis tables on the device (pg_locate_points, pg_interpolate_fields).  Output: the reference's
+results file ``<directory>/<mode>_petgemV<version>_<date>.h5`` with its schema (postprocessing.py:341-461:
+groups ``machine`` and ``model``, E/H fields per component, MT impedance / apparent resistivity / phase /
+tipper), written by ``h5lite`` (h5py is not a dependency), plus ``<directory>/fields.npz`` with the same
+arrays; the scratch files are removed afterwards like the reference does (postprocessing.py:463-472) unless
+the parameter file says ``remove_scratch: False``.
 """
 from __future__ import annotations
 
@@ -66,6 +70,75 @@ def computeImpedance(fields, omega, mu):
     return apparent_resistivity, phase, [T[:, 0], T[:, 1]], impedance
 
 
+def results_tree(inputSetup, out, total_num_dofs=None, solver_type='None', date=None):
+    """The groups and datasets of the reference's results file (postprocessing.py:346-458) as a nested dict."""
+    import platform
+    from datetime import datetime
+
+    model, run, output = inputSetup.model, inputSetup.run, inputSetup.output
+    mode = model.get('mode')
+    data_model = model.get(mode)
+    npol = run.get('num_polarizations')
+    uname = platform.uname()
+    machine = {'machine': uname.node + '. ' + uname.release + '. ' + uname.processor,
+               'num_processors': MPIEnvironment().num_proc, 'petgem_version': CODE_VERSION}
+    m = {'date': (date or datetime.today()).isoformat(), 'mesh_file': str(model.get('mesh')),
+         'receivers_file': str(model.get('receivers')), 'nord': run.get('nord'),
+         'dof': int(total_num_dofs) if total_num_dofs is not None else -1, 'cuda': bool(run.get('cuda')),
+         'vtk': bool(output.get('vtk')), 'mode': mode, 'num-polarizations': npol, 'solver': solver_type,
+         'run-time (s)': float(out.get('run_time_s', 0.0))}
+    if run.get('conductivity_from_file'):
+        m['sigma-file'] = str(data_model.get('sigma').get('file'))
+    else:
+        m['sigma_horizontal (S/m)'] = np.asarray(data_model.get('sigma').get('horizontal'), dtype=np.float64)
+        m['sigma_vertical (S/m)'] = np.asarray(data_model.get('sigma').get('vertical'), dtype=np.float64)
+    comp = ('x', 'y', 'z')
+    if mode == 'csem':
+        src = data_model.get('source')
+        m['frequency (Hz)'] = float(src.get('frequency'))
+        m['source_position (m)'] = np.asarray(src.get('position'), dtype=np.float64)
+        m['source_azimuth (deg)'] = float(src.get('azimuth'))
+        m['source_dip (deg)'] = float(src.get('dip'))
+        m['source_current (Am)'] = float(src.get('current'))
+        m['source_length (m)'] = float(src.get('length'))
+        f = out['fields_0']
+        m['E-fields'] = {c: f[:, i] for i, c in enumerate(comp)}
+        m['H-fields'] = {c: f[:, 3 + i] for i, c in enumerate(comp)}
+    else:
+        m['frequency (Hz)'] = float(data_model.get('frequency'))
+        pol = data_model.get('polarization')
+        m['polarization'] = str(pol)
+        for i in range(npol):
+            f = out['fields_%d' % i]
+            m['E-fields_mode_' + pol[i]] = {c: f[:, j] for j, c in enumerate(comp)}
+            m['H-fields_mode_' + pol[i]] = {c: f[:, 3 + j] for j, c in enumerate(comp)}
+        if 'impedance' in out:
+            four = ('xx', 'xy', 'yx', 'yy')
+            m['impedance'] = {k: out['impedance'][i] for i, k in enumerate(four)}
+            m['apparent_resistivity'] = {k: out['apparent_resistivity'][i] for i, k in enumerate(four)}
+            m['phase'] = {k: out['phase'][i] for i, k in enumerate(four)}
+            m['tipper'] = {'x': out['tipper'][0], 'y': out['tipper'][1]}
+    return {'machine': machine, 'model': m}
+
+
+CODE_VERSION = '1.0'  # postprocessing.py:333 (code_version)
+
+
+def write_results_h5(inputSetup, out):
+    """<directory>/<mode>_petgemV<version>_<date>.h5 (postprocessing.py:342-344) -> its path."""
+    from datetime import datetime
+
+    from . import h5lite
+
+    mode = inputSetup.model.get('mode')
+    path = (inputSetup.output.get('directory') + '/' + mode + '_petgemV' + CODE_VERSION + '_'
+            + str(datetime.today().strftime('%Y-%m-%d')) + '.h5')
+    opts = getattr(inputSetup, 'petsc_options', None) or {}
+    h5lite.write(path, results_tree(inputSetup, out, total_num_dofs=out.get('total_num_dofs'),
+                                    solver_type=str(opts.get('ksp_type', 'None'))))
+    return path
+
+
 class Postprocessing():
     """Class for postprocessing."""
 
@@ -90,9 +163,11 @@ class Postprocessing():
                 out.update(apparent_resistivity=np.stack(res), phase=np.stack(phase), tipper=np.stack(tipper),
                            impedance=np.stack(imp))
             out['receiver_coordinates'] = receivers
+            out['total_num_dofs'] = int(np.asarray(tab['dofs']).max()) + 1
             out['run_time_s'] = Timers().elapsed('Assembly') + Timers().elapsed('Solver')
             np.savez(inputSetup.output.get('directory') + '/fields.npz', **out)
             self.fields = out
+            self.output_file = write_results_h5(inputSetup, out)
             # scratch clean-up (postprocessing.py:463-472): the whole scratch directory when it was given
             # in the parameter file, else only the PETSc binary files written next to the results
             import os

@@ -40,21 +40,32 @@ def read_gmsh22(path):
     return pts, np.array(tets, dtype=np.int64) - 1, np.array(tags, dtype=np.int64)
 
 
-def read_receivers(path):
-    """Receiver positions: .npy / text, or the contiguous 'data' dataset of PETGEM's .h5 files
-    (h5py when available, else the raw layout of the shipped files: float64 rows at offset 2048)."""
+def read_receivers(path, cols=3, rows=None):
+    """Receiver positions [n, 3] (or another [rows, cols] float64 table such as the conductivity model):
+    .npy / text, or the contiguous 'data' dataset of PETGEM's .h5 files.  With h5py the dataset is read
+    properly; without it only the layout h5py gives the shipped single-dataset files is accepted (object
+    headers in the first 2048 bytes, then the float64 rows) and the size is checked against `cols` (and
+    `rows` when known) -- anything else fails loudly instead of being reinterpreted."""
     if path.endswith(".npy"):
         return np.load(path)
     if path.endswith(".h5"):
         try:
             import h5py
-
+        except ImportError:
+            h5py = None
+        if h5py is not None:
             with h5py.File(path, "r") as fh:
                 return fh["data"][()]
-        except ImportError:
-            raw = np.fromfile(path, dtype=np.uint8)
-            return raw[2048:2048 + ((raw.size - 2048) // 24) * 24].view("<f8").reshape(-1, 3)
-    return np.loadtxt(path).reshape(-1, 3)
+        raw = np.fromfile(path, dtype=np.uint8)
+        body = raw.size - 2048
+        if raw[:8].tobytes() != b"\x89HDF\r\n\x1a\n" or body <= 0 or body % (8 * cols) or \
+                (rows is not None and body != 8 * cols * rows):
+            Print.master("     %s: cannot be read without h5py (expected one contiguous float64 dataset of %s x %d "
+                         "values behind a 2048-byte header); install h5py or convert the file to .npy"
+                         % (path, "n" if rows is None else str(rows), cols))
+            exit(-1)
+        return raw[2048:].view("<f8").reshape(-1, cols)
+    return np.loadtxt(path).reshape(-1, cols)
 
 
 def locate_points(nodes, elemsN, points, tol=1.0e-12):
@@ -132,7 +143,7 @@ class Preprocessing():
         i_model = data_model.get('sigma')
         if run.get('conductivity_from_file'):
             sig_file = i_model.get('file')
-            conductivityModel = np.load(sig_file) if sig_file.endswith('.npy') else read_receivers(sig_file)[:, :2]
+            conductivityModel = np.load(sig_file) if sig_file.endswith('.npy') else read_receivers(sig_file, cols=2, rows=nElems)
         else:
             elemsS = tags - 1
             conductivityModel = np.stack([np.asarray(i_model.get('horizontal'), dtype=np.float64)[elemsS],

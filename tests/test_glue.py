@@ -231,6 +231,21 @@ def test_kernel_cli_end_to_end(tmp_path, topo, oracle):
     assert E.shape == Ed.shape
     assert np.abs(E[:, :3] - Ed[:, :3]).max() <= 1e-6 * np.abs(Ed[:, :3]).max()
     assert np.abs(E[:, 3:] - Ed[:, 3:]).max() <= 1e-6 * np.abs(Ed[:, 3:]).max()
+    # the reference's results file (postprocessing.py:341-461): <mode>_petgemV<version>_<date>.h5 with the
+    # groups machine / model and the receiver responses per component
+    import glob
+
+    from petgem_b200 import h5lite
+    h5 = glob.glob(str(tmp_path / "out" / "csem_petgemV*.h5"))
+    assert len(h5) == 1
+    r = h5lite.read(h5[0])
+    assert set(r) == {"machine", "model"} and r["machine"]["petgem_version"] == "1.0"
+    m = r["model"]
+    assert m["mode"] == "csem" and m["nord"] == 1 and m["dof"] == N and bool(m["cuda"])
+    assert m["solver"] == "gmres" and m["frequency (Hz)"] == 2.0 and m["num-polarizations"] == 1
+    assert np.array_equal(m["source_position (m)"], src)
+    for i, c in enumerate("xyz"):
+        assert np.array_equal(m["E-fields"][c], E[:, i]) and np.array_equal(m["H-fields"][c], E[:, 3 + i])
     # x0.dat is a PETSc binary Vec the reference Postprocessing could read (solver.py:593-594)
     from petgem_b200.parallel import readPetscVector
     x = readPetscVector(str(tmp_path / "tmp" / "x0.dat")).getArray()

@@ -203,3 +203,37 @@ def test_common_star_import():
     ns = {}
     exec("from petgem_b200.common import *", ns)
     assert "Print" in ns and "InputParameters" in ns and "Timers" in ns
+
+
+def test_h5lite_roundtrip_and_checksum(tmp_path):
+    """The HDF5 subset of the results file (postprocessing.py:341-461): lookup3 known answers (Jenkins'
+    lookup3.c self-test strings), and write -> read of every value kind the schema uses."""
+    from petgem_b200 import h5lite
+
+    s = b"Four score and seven years ago"
+    assert h5lite.lookup3(s, 0) == 0x17770551 and h5lite.lookup3(s, 1) == 0xCD628161
+    assert h5lite.lookup3(b"", 0) == 0xDEADBEEF
+    tree = {"machine": {"machine": "node. 6.1. x86_64", "num_processors": 8, "petgem_version": "1.0"},
+            "model": {"nord": 2, "cuda": True, "vtk": False, "run-time (s)": 1.25, "mode": "mt", "polarization": "xy",
+                      "source_position (m)": np.array([1750.0, 1750.0, -975.0]),
+                      "E-fields_mode_x": {"x": np.arange(7) * (1.5 - 2j), "y": np.zeros(7, dtype=complex)},
+                      "apparent_resistivity": {"xx": np.linspace(0, 1, 7)},
+                      "wide": {"k%02d" % i: i for i in range(24)}}}  # more links than libhdf5's compact default
+    f = str(tmp_path / "r.h5")
+    h5lite.write(f, tree)
+    raw = open(f, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and len(raw) % 8 == 0
+    r = h5lite.read(f)
+    assert r["machine"] == tree["machine"]
+    m = r["model"]
+    assert m["cuda"] and not m["vtk"] and m["nord"] == 2 and m["run-time (s)"] == 1.25 and m["polarization"] == "xy"
+    assert np.array_equal(m["source_position (m)"], tree["model"]["source_position (m)"])
+    assert np.array_equal(m["E-fields_mode_x"]["x"], tree["model"]["E-fields_mode_x"]["x"])
+    assert m["E-fields_mode_x"]["x"].dtype == np.complex128
+    assert [m["wide"]["k%02d" % i] for i in range(24)] == list(range(24))
+    # a flipped byte in an object header is caught by its checksum
+    bad = bytearray(raw)
+    bad[raw.index(b"OHDR") + 12] ^= 0x40
+    open(f, "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        h5lite.read(f)
