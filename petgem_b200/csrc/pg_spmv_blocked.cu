@@ -172,6 +172,82 @@ __global__ void __launch_bounds__(256) spmm_blocked2_kernel(int64_t nb, const En
     }
 }
 
+// Same work assignment, different schedule: the gathers of X depend on the column-entity indices, and with the
+// plain loop every step pays two dependent memory latencies (index, then X).  Here the 8 lanes of a group load
+// up to 32 indices of the entity at once (coalesced) and every step takes its index from a register by
+// shuffle, so all X gathers and value loads of the entity are independent of any in-flight load.
+template <int K>
+__global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
+                                                               const int32_t *__restrict__ colstart,
+                                                               const double2 *__restrict__ vals,
+                                                               const double2 *__restrict__ X,
+                                                               const double2 *__restrict__ dscale,
+                                                               double2 *__restrict__ Y, int chunk) {
+    constexpr int NS = kBG / K;  // column entities per step of a group
+    const int lane = threadIdx.x % kBG;
+    const int r = lane % K, sub = lane / K;
+    const int gpb = blockDim.x / kBG;  // in-order grid, see spmv_blocked2_kernel
+    const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
+    const uint64_t stream = l2_policy_evict_first();
+    const double2 *Xr = X + r;
+    for (int c = 0; c < chunk; ++c) {
+        const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
+        if (i >= nb) break;
+        const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
+        const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
+        const int L = (h1.x >> 16) & 0xffff;
+        const int row = h1.z, cbase = h1.w;
+        const int nc = L >> 1;
+        const double2 *v0 = vals + valoff, *v1 = v0 + L;
+        const int32_t *cs = colstart + cbase;
+        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        for (int base = 0; base < nc; base += 4 * kBG) {
+            int32_t idx[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = base + q * kBG + lane;
+                idx[q] = j < nc ? ld_stream<1>(cs + j, stream) : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (base + q * kBG >= nc) break;  // uniform over the group
+#pragma unroll
+                for (int s0 = 0; s0 < kBG; s0 += NS) {
+                    const int jl = s0 + sub;                       // position inside this 8-block of column entities
+                    const int32_t c0 = __shfl_sync(gm, idx[q], jl, kBG);
+                    const int j = base + q * kBG + jl;
+                    if (j < nc) {
+                        const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
+                        const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+                        const double2 x0 = __ldg(Xr + (int64_t)c0 * K), x1 = __ldg(Xr + ((int64_t)c0 + 1) * K);
+                        cfma2(a0, p00, x0);
+                        cfma2(a1, p10, x0);
+                        cfma2(a0, p01, x1);
+                        cfma2(a1, p11, x1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = K; o < kBG; o <<= 1) {  // sum over the lane sets that share right-hand side r
+            a0.x += __shfl_xor_sync(gm, a0.x, o, kBG);
+            a0.y += __shfl_xor_sync(gm, a0.y, o, kBG);
+            a1.x += __shfl_xor_sync(gm, a1.x, o, kBG);
+            a1.y += __shfl_xor_sync(gm, a1.y, o, kBG);
+        }
+        if (sub == 0) {
+            if (dscale) {
+                const double2 d0 = __ldg(dscale + row), d1 = __ldg(dscale + row + 1);
+                a0 = make_double2(d0.x * a0.x - d0.y * a0.y, d0.x * a0.y + d0.y * a0.x);
+                a1 = make_double2(d1.x * a1.x - d1.y * a1.y, d1.x * a1.y + d1.y * a1.x);
+            }
+            Y[(int64_t)row * K + r] = a0;
+            Y[((int64_t)row + 1) * K + r] = a1;
+        }
+    }
+}
+
 // Variant with one lane per column entity and all K right-hand sides in that lane (2K accumulators):
 // no value is loaded twice.  Measured at C3: better at K = 2 (7.3 vs 7.6 ms), worse at K = 4 (12.8 vs
 // 10.6 ms, registers), so it serves K = 2 only.
@@ -288,10 +364,19 @@ extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(Y);
     cudaStream_t st = (cudaStream_t)stream;
+    static const int pf = [] {  // PG_SPMM_PF=1: index-prefetch schedule (spmm_blocked2_pf_kernel)
+        const char *e = getenv("PG_SPMM_PF");
+        return e ? atoi(e) : 0;
+    }();
     switch (k) {
         case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        case 4: spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        default: spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+        case 4:
+            if (pf) spmm_blocked2_pf_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            break;
+        default:
+            if (pf) spmm_blocked2_pf_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
     return PG_OK;

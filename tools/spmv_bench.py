@@ -15,8 +15,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=64)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--morton", type=int, default=0)
+ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity in bytes (32, 64, 128; 0 = default)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
+torch.zeros(1, device=dev)
+if args.l2_fetch:
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so")
+    val = ctypes.c_size_t(0)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch))  # cudaLimitMaxL2FetchGranularity
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print("cudaLimitMaxL2FetchGranularity -> rc %d, now %d" % (rc, val.value))
 tab = bench.build_case(args.m, 2)
 rows = bench.host_rows(tab)
 el = ElementData(rows["nodes"], rows["elemsN"], rows["elemsE"], rows["edgesNodes"], rows["facesEdges"], rows["elemsF"],
@@ -52,6 +61,7 @@ for name, A in (("csr", CSRMatrix(rowptr, colidx, vals, plan.N)),
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
     out[name] = (ms, (20.0 * plan.nnz + 40.0 * plan.N) / ms / 1e6)
+print("pf=%s l2fetch=%d " % (os.environ.get("PG_SPMM_PF", "0"), args.l2_fetch), end="")
 print("hints=%s morton=%d m=%d nnz=%d assemble %.3f ms:" % (os.environ.get("PG_SPMV_HINTS", "1"), args.morton, args.m,
                                                             plan.nnz, asm_ms),
       " ".join("%s %.3f ms %.0f GB/s" % (k, v[0], v[1]) for k, v in out.items()))
