@@ -97,6 +97,18 @@ int pg_shape_functions_host(int p, uint32_t code, const double *xi_host, double 
 int pg_element_matrices(int64_t T, int p, const double *geo, const uint32_t *code, const double *table,
                         double *Me, double *Ke, void *stream);
 
+/* The same Me, Ke as two n x n x 3*ngauss products per element on the FP64 tensor pipe (mma.sync.m8n8k4.f64,
+ * SASS DMMA): Me = sign(detJ) U^T U, Ke = sign(detJ) V^T V with the mapped, weighted basis values at the Gauss
+ * points as U, V (the literal form of the loops at hvfem.py:288-314).  Kept for the A/B against the table
+ * contraction (tools/dmma_ab.py, profiles/r2_dmma_ab.json); pg_assemble does not use it.
+ *   nodes [T,12], sigma [T,2], code [T] as for pg_element_geometry; phiN, phiC [nexp, ngauss, 3] f64: the
+ *   orientation-expanded reference functions / curls at the Gauss points; weights [ngauss] (sum 1/6);
+ *   work: pg_phi_gemm_workspace_doubles(T, p, ngauss) doubles; stage 0 = both, 1 = operands only, 2 = GEMMs only. */
+int64_t pg_phi_gemm_workspace_doubles(int64_t T, int p, int ngauss);
+int pg_element_matrices_phi_gemm(int64_t T, int p, const double *nodes, const double *sigma, const uint32_t *code,
+                                 int ngauss, const double *phiN, const double *phiC, const double *weights,
+                                 double *work, int stage, double *Me, double *Ke, void *stream);
+
 /* solver.py:223-224: Ae = K - i*omega*mu*M, flattened row-major; mass_scale = -omega*mu.
  *   Ae [T,n,n] complex128 */
 int pg_element_systems(int64_t T, int p, const double *geo, const uint32_t *code, const double *table,
@@ -397,6 +409,22 @@ int pg_graph_begin(void *stream);
 int pg_graph_end(void *stream, void **graph_exec);
 int pg_graph_launch(void *graph_exec, void *stream);
 void pg_graph_destroy(void *graph_exec);
+
+/* L2 residency of the vector MatMult gathers from (x is re-read ~20 times per entry, the matrix streams once).
+ * pg_l2_persist: access-policy window on `stream` over [ptr, ptr+bytes): lines of the window are kept in the
+ *   persisting set-aside of the L2 (all of them when the window fits pg_l2_persist_capacity(), else the
+ *   fraction hit_ratio, 0 = capacity / bytes), everything else streams; ptr NULL clears the window and resets
+ *   the persisting lines.  Applies to the kernels launched on the stream afterwards (captured graphs keep it).
+ * pg_l2_fetch_granularity: cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes; scattered 32-byte gathers).
+ * pg_tune_spmv_hints: per-load eviction hints of the MatMult kernels (0: ld.cs streams; 1: evict-first
+ *   streams, the default; 2: evict-first streams + evict-last x; -1: PG_SPMV_HINTS / default). */
+int pg_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream);
+int64_t pg_l2_persist_capacity(void);
+int pg_l2_fetch_granularity(int bytes);
+int pg_tune_spmv_hints(int mode);
+/* schedule of pg_spmm_blocked (k = 4, 8): 1 = the column-entity indices of a row entity are loaded up front and
+ * handed out by shuffle (no index -> gather dependency per step), 0 = plain loop, -1 = PG_SPMM_PF / default */
+int pg_tune_spmm_prefetch(int mode);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpetgem_b200.so")
-SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu", "pg_tables.cu", "pg_comm.cu"]
+SOURCES = ["pg_element.cu", "pg_plan.cu", "pg_assemble.cu", "pg_linalg.cu", "pg_spmv_blocked.cu", "pg_multi.cu", "pg_krylov.cu", "pg_aux.cu", "pg_tables.cu", "pg_comm.cu", "pg_dmma.cu"]
 HEADERS = ["pg_common.cuh", "pg_plan.cuh", "pg_basis.cuh", os.path.join("..", "..", "include", "petgem_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -171,6 +171,13 @@ SIGNATURES = {
     "pg_comm_wait": (C.c_int, [_p, _i32, C.c_uint32, _p]),
     "pg_comm_ack": (C.c_int, [_p, _i32, C.c_uint32, _p]),
     "pg_comm_status": (C.c_int, [_p, _p]),
+    "pg_l2_persist": (C.c_int, [_p, _i64, _d, _p]),
+    "pg_l2_persist_capacity": (_i64, []),
+    "pg_l2_fetch_granularity": (C.c_int, [_i32]),
+    "pg_tune_spmv_hints": (C.c_int, [_i32]),
+    "pg_tune_spmm_prefetch": (C.c_int, [_i32]),
+    "pg_phi_gemm_workspace_doubles": (_i64, [_i64, _i32, _i32]),
+    "pg_element_matrices_phi_gemm": (C.c_int, [_i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -177,7 +177,8 @@ template <int HINT>
 __device__ __forceinline__ double2 ld_keep(const double2 *p, uint64_t keep) {
     return HINT == 2 ? ld_hint(p, keep) : __ldg(p);
 }
-int spmv_hint_mode();  // PG_SPMV_HINTS environment variable (default 1), read once
+int spmv_hint_mode();  // PG_SPMV_HINTS environment variable (default 1), read once; pg_tune overrides
+void set_spmv_hint_mode(int mode);
 
 template <typename F>
 int dispatch_order(int p, F &&f) {

@@ -315,13 +315,15 @@ __global__ void __launch_bounds__(256) zcopy_scaled_kernel(int64_t n, const doub
         y[i] = cmul(al, x[i]);
 }
 
+static int g_spmv_hint_override = -1;
 int spmv_hint_mode() {
     static const int mode = [] {
         const char *e = getenv("PG_SPMV_HINTS");
         return e ? atoi(e) : 1;  // measured (tools/spmv_bench.py): explicit evict-first on the streams wins
     }();
-    return mode;
+    return g_spmv_hint_override >= 0 ? g_spmv_hint_override : mode;
 }
+void set_spmv_hint_mode(int mode) { g_spmv_hint_override = mode; }
 
 static inline unsigned ew_grid(int64_t n) {
     int64_t b = (n + 255) / 256;

@@ -7,6 +7,8 @@
 // the gather of column c fetches 16*K contiguous bytes, and every element-wise kernel finds the
 // right-hand side of element e as e & (K-1).  Reductions are fixed two-stage trees per right-hand
 // side (bit-reproducible), scalars stay on the device.
+#include <string.h>
+
 #include <algorithm>
 
 #include "pg_common.cuh"
@@ -465,6 +467,58 @@ int pg_graph_launch(void *graph_exec, void *stream) {
 
 void pg_graph_destroy(void *graph_exec) {
     if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+}
+
+// ---- L2 residency of the vector MatMult gathers from --------------------------------------------------------
+int pg_tune_spmv_hints(int mode) {
+    PG_REQUIRE(mode >= -1 && mode <= 2, PG_EINVAL, "pg_tune_spmv_hints: mode %d (-1 = environment default, 0..2)", mode);
+    set_spmv_hint_mode(mode);
+    return PG_OK;
+}
+
+int pg_l2_fetch_granularity(int bytes) {
+    PG_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, PG_EINVAL, "pg_l2_fetch_granularity: %d (32, 64, 128)", bytes);
+    PG_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return PG_OK;
+}
+
+int pg_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (!ptr || bytes <= 0) {  // clear the window and release the persisting lines
+        attr.accessPolicyWindow.base_ptr = nullptr;
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitRatio = 0.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        PG_CUDA_OK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        PG_CUDA_OK(cudaCtxResetPersistingL2Cache());
+        return PG_OK;
+    }
+    int dev = 0, max_persist = 0, max_window = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    PG_CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    PG_CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    PG_REQUIRE(max_persist > 0 && max_window > 0, PG_ECUDA, "pg_l2_persist: the device has no persisting L2");
+    const size_t window = (size_t)std::min<int64_t>(bytes, max_window);
+    PG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+    attr.accessPolicyWindow.num_bytes = window;
+    // lines of the window that are kept: all of it when it fits the set-aside, else that fraction
+    float ratio = hit_ratio > 0.0 ? (float)hit_ratio : std::min(1.0f, (float)max_persist / (float)window);
+    attr.accessPolicyWindow.hitRatio = ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    PG_CUDA_OK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return PG_OK;
+}
+
+int64_t pg_l2_persist_capacity(void) {
+    int dev = 0, max_persist = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) return 0;
+    return max_persist;
 }
 
 }  // extern "C"

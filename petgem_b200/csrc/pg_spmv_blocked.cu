@@ -324,6 +324,12 @@ __global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, con
 
 using namespace pg;
 
+static int g_spmm_pf = -1;
+extern "C" int pg_tune_spmm_prefetch(int mode) {
+    g_spmm_pf = mode;
+    return PG_OK;
+}
+
 extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const double *vals, const double *x,
                                const double *dscale, double *y, void *stream) {
     PG_REQUIRE(pl && vals && x && y, PG_EINVAL, "pg_spmv_blocked: null pointer");
@@ -364,10 +370,11 @@ extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(Y);
     cudaStream_t st = (cudaStream_t)stream;
-    static const int pf = [] {  // PG_SPMM_PF=1: index-prefetch schedule (spmm_blocked2_pf_kernel)
+    static const int pf_env = [] {  // PG_SPMM_PF=1: index-prefetch schedule (spmm_blocked2_pf_kernel)
         const char *e = getenv("PG_SPMM_PF");
         return e ? atoi(e) : 0;
     }();
+    const int pf = g_spmm_pf >= 0 ? g_spmm_pf : pf_env;
     switch (k) {
         case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         case 4:
