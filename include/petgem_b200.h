@@ -417,11 +417,13 @@ void pg_graph_destroy(void *graph_exec);
  *   the persisting lines.  Applies to the kernels launched on the stream afterwards (captured graphs keep it).
  * pg_l2_fetch_granularity: cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes; scattered 32-byte gathers).
  * pg_tune_spmv_hints: per-load eviction hints of the MatMult kernels (0: ld.cs streams; 1: evict-first
- *   streams, the default; 2: evict-first streams + evict-last x; -1: PG_SPMV_HINTS / default). */
+ *   streams, the default; 2: evict-first streams + evict-last x; 3: as 1 and the streams are not allocated in L1; -1: PG_SPMV_HINTS /
+ *   default).  pg_tune_spmv_chunk: consecutive 32-entity tiles per thread block of pg_spmv_blocked. */
 int pg_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream);
 int64_t pg_l2_persist_capacity(void);
 int pg_l2_fetch_granularity(int bytes);
 int pg_tune_spmv_hints(int mode);
+int pg_tune_spmv_chunk(int chunk);
 /* schedule of pg_spmm_blocked (k = 4, 8): 1 = the column-entity indices of a row entity are loaded up front and
  * handed out by shuffle (no index -> gather dependency per step), 0 = plain loop, -1 = PG_SPMM_PF / default */
 int pg_tune_spmm_prefetch(int mode);

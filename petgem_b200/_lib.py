@@ -176,6 +176,7 @@ SIGNATURES = {
     "pg_l2_fetch_granularity": (C.c_int, [_i32]),
     "pg_tune_spmv_hints": (C.c_int, [_i32]),
     "pg_tune_spmm_prefetch": (C.c_int, [_i32]),
+    "pg_tune_spmv_chunk": (C.c_int, [_i32]),
     "pg_phi_gemm_workspace_doubles": (_i64, [_i64, _i32, _i32]),
     "pg_element_matrices_phi_gemm": (C.c_int, [_i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -163,15 +163,49 @@ __device__ __forceinline__ int32_t ld_hint(const int32_t *ptr, uint64_t policy) 
     return v;
 }
 
+// the same, and the line is not allocated in L1: the matrix streams (20 MB per SM and pass) would otherwise
+// push the x entries out of the 256 KB L1 that serves ~2/3 of the x gathers
+__device__ __forceinline__ double2 ld_hint_na(const double2 *ptr, uint64_t policy) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_hint_na(const int32_t *ptr, uint64_t policy) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
+    return v;
+}
+
+// 256-bit loads (sm_100: LDG.E.256): a 2x1 block of complex values -- one 32-byte sector -- in ONE request.
+// With two 16-byte loads per sector both requests miss L1 while the first is in flight, the L2 serves the
+// first and evicts the evict-first line, and the second goes to DRAM again: ncu on the blocked SpMV at C3
+// counted 1.41 G sector requests from L1 and 30.4 GB of DRAM reads for 24.5 GB of matrix.
+struct __align__(32) double2x2 {
+    double2 a, b;
+};
+__device__ __forceinline__ double2x2 ld256_stream(const double2 *ptr, uint64_t policy) {
+    double2x2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(ptr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double2x2 ld256(const double2 *ptr) {
+    double2x2 v;
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(ptr));
+    return v;
+}
+
 // HINT = 0: default policy for x, evict-first (ld.cs) for the streams; 1: explicit evict-first policy
-// on the streams only; 2: evict-first on the streams and evict-last on x
+// on the streams only; 2: evict-first on the streams and evict-last on x; 3: as 1, streams bypass L1
 template <int HINT>
 __device__ __forceinline__ double2 ld_stream(const double2 *p, uint64_t stream) {
-    return HINT == 0 ? __ldcs(p) : ld_hint(p, stream);
+    return HINT == 0 ? __ldcs(p) : HINT == 3 ? ld_hint_na(p, stream) : ld_hint(p, stream);
 }
 template <int HINT>
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p, uint64_t stream) {
-    return HINT == 0 ? __ldcs(p) : ld_hint(p, stream);
+    return HINT == 0 ? __ldcs(p) : HINT == 3 ? ld_hint_na(p, stream) : ld_hint(p, stream);
 }
 template <int HINT>
 __device__ __forceinline__ double2 ld_keep(const double2 *p, uint64_t keep) {

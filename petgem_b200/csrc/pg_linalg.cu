@@ -319,7 +319,9 @@ static int g_spmv_hint_override = -1;
 int spmv_hint_mode() {
     static const int mode = [] {
         const char *e = getenv("PG_SPMV_HINTS");
-        return e ? atoi(e) : 1;  // measured (tools/spmv_bench.py): explicit evict-first on the streams wins
+        // measured (tools/spmv_probe.py, profiles/r2_spmv_l2_probe.jsonl): explicit evict-first on the streams (1)
+        // beats ld.cs (0), evict-last x (2) and L1 bypass (3); 256-bit sector loads on top of it (4) win 7-10 %
+        return e ? atoi(e) : 4;
     }();
     return g_spmv_hint_override >= 0 ? g_spmv_hint_override : mode;
 }
@@ -355,8 +357,11 @@ int pg_spmv_scaled(int64_t rows, const int64_t *rowptr, const int32_t *colidx, c
     constexpr int G = 8;
     int64_t blocks = std::min<int64_t>((rows * G + 255) / 256, (int64_t)kNumSMs * 96);
     switch (spmv_hint_mode()) {
-        case 1: spmv_kernel<G, 1><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
+        case 1:
+        case 4:  // the CSR kernel reads whole sectors per request already (consecutive lanes, 16 B each)
+            spmv_kernel<G, 1><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
         case 2: spmv_kernel<G, 2><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
+        case 3: spmv_kernel<G, 3><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y)); break;
         default: spmv_kernel<G, 0><<<(unsigned)blocks, 256, 0, st>>>(rows, rowptr, colidx, CD2(vals), CD2(x), CD2(dscale), D2(y));
     }
     PG_LAUNCH_OK();

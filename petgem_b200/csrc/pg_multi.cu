@@ -471,7 +471,7 @@ void pg_graph_destroy(void *graph_exec) {
 
 // ---- L2 residency of the vector MatMult gathers from --------------------------------------------------------
 int pg_tune_spmv_hints(int mode) {
-    PG_REQUIRE(mode >= -1 && mode <= 2, PG_EINVAL, "pg_tune_spmv_hints: mode %d (-1 = environment default, 0..2)", mode);
+    PG_REQUIRE(mode >= -1 && mode <= 4, PG_EINVAL, "pg_tune_spmv_hints: mode %d (-1 = environment default, 0..4)", mode);
     set_spmv_hint_mode(mode);
     return PG_OK;
 }
@@ -494,6 +494,7 @@ int pg_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream
         attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
         PG_CUDA_OK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
         PG_CUDA_OK(cudaCtxResetPersistingL2Cache());
+        PG_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));  // give the set-aside back to the normal L2
         return PG_OK;
     }
     int dev = 0, max_persist = 0, max_window = 0;

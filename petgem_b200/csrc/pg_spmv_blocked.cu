@@ -95,6 +95,74 @@ __global__ void __launch_bounds__(256, 6) spmv_blocked2_kernel(int64_t nb, const
     }
 }
 
+// The same kernel with 256-bit loads: every 2x1 block of values and every (x[c], x[c+1]) pair is ONE request for
+// ONE 32-byte sector (all of them are 32-byte aligned: rows hold an even number of entries, entities start on
+// even dofs, the halo keeps the two dofs of a column entity adjacent).
+__global__ void __launch_bounds__(256, 6) spmv_blocked2_v256_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
+                                                                    const int32_t *__restrict__ colstart,
+                                                                    const double2 *__restrict__ vals,
+                                                                    const double2 *__restrict__ x,
+                                                                    const double2 *__restrict__ dscale,
+                                                                    double2 *__restrict__ y, int chunk) {
+    const int lane = threadIdx.x % kBG;
+    const int gpb = blockDim.x / kBG;  // in-order grid, see spmv_blocked2_kernel
+    const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
+    const uint64_t stream = l2_policy_evict_first();
+    for (int c = 0; c < chunk; ++c) {
+        const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
+        if (i >= nb) break;
+        const int4 *hp = reinterpret_cast<const int4 *>(hdr + i);
+        const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const int64_t valoff = ((int64_t)(unsigned)h0.x) | ((int64_t)h0.y << 32);
+        const int L = (h1.x >> 16) & 0xffff;
+        const int row = h1.z, cbase = h1.w;
+        const int nc = L >> 1;
+        const double2 *v0 = vals + valoff, *v1 = v0 + L;
+        const int32_t *cs = colstart + cbase;
+        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        int j = lane;
+        for (; j + kBG < nc; j += 2 * kBG) {  // two column entities per lane in flight
+            const int32_t c0 = ld_stream<1>(cs + j, stream), c1 = ld_stream<1>(cs + j + kBG, stream);
+            const double2x2 p0 = ld256_stream(v0 + 2 * j, stream), p1 = ld256_stream(v1 + 2 * j, stream);
+            const double2x2 q0 = ld256_stream(v0 + 2 * (j + kBG), stream), q1 = ld256_stream(v1 + 2 * (j + kBG), stream);
+            const double2x2 xx = ld256(x + c0), zz = ld256(x + c1);
+            cfma2(a0, p0.a, xx.a);
+            cfma2(a1, p1.a, xx.a);
+            cfma2(a0, p0.b, xx.b);
+            cfma2(a1, p1.b, xx.b);
+            cfma2(a0, q0.a, zz.a);
+            cfma2(a1, q1.a, zz.a);
+            cfma2(a0, q0.b, zz.b);
+            cfma2(a1, q1.b, zz.b);
+        }
+        if (j < nc) {
+            const int32_t c0 = ld_stream<1>(cs + j, stream);
+            const double2x2 p0 = ld256_stream(v0 + 2 * j, stream), p1 = ld256_stream(v1 + 2 * j, stream);
+            const double2x2 xx = ld256(x + c0);
+            cfma2(a0, p0.a, xx.a);
+            cfma2(a1, p1.a, xx.a);
+            cfma2(a0, p0.b, xx.b);
+            cfma2(a1, p1.b, xx.b);
+        }
+#pragma unroll
+        for (int o = kBG / 2; o > 0; o >>= 1) {
+            a0.x += __shfl_down_sync(gm, a0.x, o, kBG);
+            a0.y += __shfl_down_sync(gm, a0.y, o, kBG);
+            a1.x += __shfl_down_sync(gm, a1.x, o, kBG);
+            a1.y += __shfl_down_sync(gm, a1.y, o, kBG);
+        }
+        if (lane == 0) {
+            if (dscale) {
+                const double2 d0 = __ldg(dscale + row), d1 = __ldg(dscale + row + 1);
+                a0 = make_double2(d0.x * a0.x - d0.y * a0.y, d0.x * a0.y + d0.y * a0.x);
+                a1 = make_double2(d1.x * a1.x - d1.y * a1.y, d1.x * a1.y + d1.y * a1.x);
+            }
+            y[row] = a0;
+            y[row + 1] = a1;
+        }
+    }
+}
+
 // The same for K interleaved right-hand sides (X[i*K + r], see pg_multi.cu): K lanes share a 2x2 block,
 // lane r of them gathers X[c0, r] and X[c0+1, r] -- together the 32*K contiguous bytes of the column
 // entity, which serve 4 nonzeros x K right-hand sides (8 B gathered per nonzero and right-hand side instead
@@ -176,7 +244,7 @@ __global__ void __launch_bounds__(256) spmm_blocked2_kernel(int64_t nb, const En
 // plain loop every step pays two dependent memory latencies (index, then X).  Here the 8 lanes of a group load
 // up to 32 indices of the entity at once (coalesced) and every step takes its index from a register by
 // shuffle, so all X gathers and value loads of the entity are independent of any in-flight load.
-template <int K>
+template <int K, int HINT>
 __global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
                                                                const int32_t *__restrict__ colstart,
                                                                const double2 *__restrict__ vals,
@@ -207,7 +275,7 @@ __global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int j = base + q * kBG + lane;
-                idx[q] = j < nc ? ld_stream<1>(cs + j, stream) : 0;
+                idx[q] = j < nc ? ld_stream<(HINT == 4 ? 1 : HINT)>(cs + j, stream) : 0;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -218,8 +286,14 @@ __global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const
                     const int32_t c0 = __shfl_sync(gm, idx[q], jl, kBG);
                     const int j = base + q * kBG + jl;
                     if (j < nc) {
-                        const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
-                        const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+                        double2 p00, p01, p10, p11;
+                        if (HINT == 4) {  // one request per 32-byte sector of values
+                            const double2x2 p0 = ld256_stream(v0 + 2 * j, stream), p1 = ld256_stream(v1 + 2 * j, stream);
+                            p00 = p0.a, p01 = p0.b, p10 = p1.a, p11 = p1.b;
+                        } else {
+                            p00 = ld_stream<HINT>(v0 + 2 * j, stream), p01 = ld_stream<HINT>(v0 + 2 * j + 1, stream);
+                            p10 = ld_stream<HINT>(v1 + 2 * j, stream), p11 = ld_stream<HINT>(v1 + 2 * j + 1, stream);
+                        }
                         const double2 x0 = __ldg(Xr + (int64_t)c0 * K), x1 = __ldg(Xr + ((int64_t)c0 + 1) * K);
                         cfma2(a0, p00, x0);
                         cfma2(a1, p10, x0);
@@ -278,12 +352,18 @@ __global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, con
         for (int r = 0; r < K; ++r) a0[r] = a1[r] = make_double2(0.0, 0.0);
         for (int j = lane; j < nc; j += kBG) {
             const int32_t c0 = ld_stream<1>(cs + j, stream);
-            const double2 p00 = ld_stream<1>(v0 + 2 * j, stream), p01 = ld_stream<1>(v0 + 2 * j + 1, stream);
-            const double2 p10 = ld_stream<1>(v1 + 2 * j, stream), p11 = ld_stream<1>(v1 + 2 * j + 1, stream);
+            // one request per 32-byte sector (see ld256_stream); callers pass 32-byte aligned arrays
+            const double2x2 p0 = ld256_stream(v0 + 2 * j, stream), p1 = ld256_stream(v1 + 2 * j, stream);
+            const double2 p00 = p0.a, p01 = p0.b, p10 = p1.a, p11 = p1.b;
             const double2 *xp = X + (int64_t)c0 * K;
             double2 x0[K], x1[K];
+            if (K == 2) {
+                const double2x2 xa = ld256(xp), xb = ld256(xp + 2);
+                x0[0] = xa.a, x0[K - 1] = xa.b, x1[0] = xb.a, x1[K - 1] = xb.b;
+            } else {
 #pragma unroll
-            for (int r = 0; r < K; ++r) x0[r] = __ldg(xp + r), x1[r] = __ldg(xp + K + r);
+                for (int r = 0; r < K; ++r) x0[r] = __ldg(xp + r), x1[r] = __ldg(xp + K + r);
+            }
 #pragma unroll
             for (int r = 0; r < K; ++r) {
                 cfma2(a0[r], p00, x0[r]);
@@ -325,6 +405,11 @@ __global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, con
 using namespace pg;
 
 static int g_spmm_pf = -1;
+static int g_spmv_chunk = 0;
+extern "C" int pg_tune_spmv_chunk(int chunk) {  // consecutive 32-entity tiles per block of pg_spmv_blocked
+    g_spmv_chunk = chunk;
+    return PG_OK;
+}
 extern "C" int pg_tune_spmm_prefetch(int mode) {
     g_spmm_pf = mode;
     return PG_OK;
@@ -336,16 +421,20 @@ extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const
     PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmv_blocked: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
     const int64_t nb = pl->b1 - pl->b0;
     if (nb == 0) return PG_OK;
-    const int chunk = 1;
+    const int chunk = g_spmv_chunk > 0 ? g_spmv_chunk : 1;
     const int64_t tiles = (nb * kBG + 255) / 256, blocks = (tiles + chunk - 1) / chunk;
     const int32_t *cs = colstart ? colstart : pl->colstart;
     const double2 *v2 = reinterpret_cast<const double2 *>(vals), *x2 = reinterpret_cast<const double2 *>(x);
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(y);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (spmv_hint_mode()) {
+    int mode = spmv_hint_mode();
+    if (mode == 4 && (((uintptr_t)vals | (uintptr_t)x) & 31)) mode = 1;  // 256-bit loads need 32-byte aligned arrays
+    switch (mode) {
         case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 3: spmv_blocked2_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 4: spmv_blocked2_v256_kernel<<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
@@ -370,19 +459,26 @@ extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const
     const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
     double2 *y2 = reinterpret_cast<double2 *>(Y);
     cudaStream_t st = (cudaStream_t)stream;
-    static const int pf_env = [] {  // PG_SPMM_PF=1: index-prefetch schedule (spmm_blocked2_pf_kernel)
+    // index-prefetch schedule (spmm_blocked2_pf_kernel) by default: measured at C3, k = 4: 10.96 -> 9.34 ms on the
+    // whole matrix, 1.50 -> 1.23 ms on a 1/8 row block, bit-identical results (profiles/r2_spmv_l2_probe.jsonl);
+    // PG_SPMM_PF=0 selects the plain loop
+    static const int pf_env = [] {
         const char *e = getenv("PG_SPMM_PF");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 1;
     }();
     const int pf = g_spmm_pf >= 0 ? g_spmm_pf : pf_env;
     switch (k) {
         case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         case 4:
-            if (pf) spmm_blocked2_pf_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<4, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<4, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else if (pf) spmm_blocked2_pf_kernel<4, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
             else spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
             break;
         default:
-            if (pf) spmm_blocked2_pf_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<8, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<8, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            else if (pf) spmm_blocked2_pf_kernel<8, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
             else spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();

@@ -28,6 +28,9 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--k", type=int, default=4, help="right-hand sides of the SpMM probes")
 ap.add_argument("--only", default="both", choices=["both", "block", "whole"])
 ap.add_argument("--quick", action="store_true", help="baseline MatMult only (for ncu captures)")
+ap.add_argument("--quick-floor", action="store_true", help="with --quick: the x-free variant")
+ap.add_argument("--persist", action="store_true", help="also the access-policy-window runs (measured slower)")
+ap.add_argument("--fetch", action="store_true", help="also the L2 fetch granularity runs (measured neutral)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 L = lib()
@@ -93,43 +96,63 @@ def probe(label, world, rank):
         print(json.dumps(d), flush=True)
 
     if args.quick:
-        emit("hints=1", timed(lambda: A.mult(x, y), 2))
+        if args.quick_floor:
+            A = CSRMatrix(rowptr, colidx, vals, nx, lo, plan=plan, colstart=(cs32 & 0x1FFE).contiguous(), blocked=True)
+        emit("hints=1" + (" floor" if args.quick_floor else ""), timed(lambda: A.mult(x, y), 2))
         return
-    for mode in (1, 0, 2):
+    # reference points: a pure read stream over the matrix values, and a copy of them
+    wk = torch.empty((L.pg_reduce_workspace_bytes(1) // 16,), dtype=torch.complex128, device=dev)
+    o1 = torch.zeros((1,), dtype=torch.complex128, device=dev)
+    ms = timed(lambda: check(L.pg_dznrm2sq(nnz, ptr(vals), ptr(o1), ptr(wk), stream_ptr())), args.reps)
+    emit("pure read stream over vals (pg_dznrm2sq)", ms, read_gbs=round(16.0 * nnz / ms / 1e6, 1))
+    if world > 1:
+        v2 = torch.empty_like(vals)
+        ms = timed(lambda: v2.copy_(vals), args.reps)
+        emit("copy of vals (torch)", ms, read_plus_write_gbs=round(32.0 * nnz / ms / 1e6, 1))
+        del v2
+    for mode in (1, 4, 1, 4, 0, 2, 3):
         check(L.pg_tune_spmv_hints(mode))
         emit("hints=%d" % mode, timed(lambda: A.mult(x, y), args.reps))
+    for mode in (4,):
+        check(L.pg_tune_spmv_hints(mode))
+        for chunk in (2, 4):
+            check(L.pg_tune_spmv_chunk(chunk))
+            emit("hints=%d chunk=%d" % (mode, chunk), timed(lambda: A.mult(x, y), args.reps))
+        check(L.pg_tune_spmv_chunk(1))
     check(L.pg_tune_spmv_hints(1))
-    for gran in (32, 128, 64):
-        check(L.pg_l2_fetch_granularity(gran))
-        emit("l2_fetch=%d" % gran, timed(lambda: A.mult(x, y), args.reps))
-    # x kept in the persisting part of the L2 (side stream: the window is a stream attribute)
+    if args.fetch:
+        for gran in (32, 128, 64):
+            check(L.pg_l2_fetch_granularity(gran))
+            emit("l2_fetch=%d" % gran, timed(lambda: A.mult(x, y), args.reps))
     side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        for mode in (1, 2):
-            check(L.pg_tune_spmv_hints(mode))
-            check(L.pg_l2_persist(ptr(x), nx * 16, 0.0, stream_ptr()))
-            emit("persist window on x, hints=%d" % mode, timed(lambda: A.mult(x, y), args.reps))
-            check(L.pg_l2_persist(None, 0, 0.0, stream_ptr()))
-    check(L.pg_tune_spmv_hints(1))
+    if args.persist:  # x kept in the persisting part of the L2 (side stream: the window is a stream attribute)
+        with torch.cuda.stream(side):
+            for mode in (1, 2):
+                check(L.pg_tune_spmv_hints(mode))
+                check(L.pg_l2_persist(ptr(x), nx * 16, 0.0, stream_ptr()))
+                emit("persist window on x, hints=%d" % mode, timed(lambda: A.mult(x, y), args.reps))
+                check(L.pg_l2_persist(None, 0, 0.0, stream_ptr()))
+        check(L.pg_tune_spmv_hints(1))
     # floor: (almost) no x traffic: every gather lands in the first 128 KB of x (spread over 4096 sector pairs;
     # a single entry would serialise on one L2 slice: measured 0.91 ms against 0.64 ms for the real pattern)
     A0 = CSRMatrix(rowptr, colidx, vals, nx, lo, plan=plan, colstart=(cs32 & 0x1FFE).contiguous(), blocked=True)
-    emit("floor: all gathers inside 128 KB of x", timed(lambda: A0.mult(x, y), args.reps))
+    for mode in (1, 4):
+        check(L.pg_tune_spmv_hints(mode))
+        emit("floor (all gathers inside 128 KB of x), hints=%d" % mode, timed(lambda: A0.mult(x, y), args.reps))
+    check(L.pg_tune_spmv_hints(1))
     # four right-hand sides
     k = args.k
     X = torch.randn((nx, k), dtype=torch.complex128, device=dev)
     Y = torch.empty((n, k), dtype=torch.complex128, device=dev)
-    for pf in (0, 1):
+    for pf, mode in ((0, 1), (1, 1), (1, 4), (1, 3)):
         check(L.pg_tune_spmm_prefetch(pf))
-        emit("spmm k=%d prefetch=%d" % (k, pf), timed(lambda: A.mult_multi(X, Y), args.reps))
+        check(L.pg_tune_spmv_hints(mode))
+        emit("spmm k=%d prefetch=%d hints=%d" % (k, pf, mode), timed(lambda: A.mult_multi(X, Y), args.reps))
         if pf == 0:
             Yref = Y.clone()
     emit("spmm prefetch parity", 0.0, max_rel_diff=float((Y - Yref).abs().max() / Yref.abs().max()))
-    with torch.cuda.stream(side):
-        check(L.pg_l2_persist(ptr(X), nx * 16 * k, 0.0, stream_ptr()))
-        emit("spmm k=%d, persist window on X" % k, timed(lambda: A.mult_multi(X, Y), args.reps))
-        check(L.pg_l2_persist(None, 0, 0.0, stream_ptr()))
-    emit("spmm k=%d floor" % k, timed(lambda: A0.mult_multi(X, Y), args.reps))
+    emit("spmm k=%d floor (prefetch=1 hints=3)" % k, timed(lambda: A0.mult_multi(X, Y), args.reps))
+    check(L.pg_tune_spmv_hints(1))
 
 
 if args.only in ("both", "block"):
