@@ -49,39 +49,12 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t rows, const int64_t *
 #pragma unroll
         for (int r = 0; r < K; ++r) acc[r] = make_double2(0.0, 0.0);
         int64_t j = a + lane;
-        if (K == 2) {
-            // four independent (index, value, gather) streams per lane; the two right-hand sides of a column are
-            // one 32-byte sector: ONE 256-bit request (two 16-byte loads would both miss L1 and reach the L2 twice)
-            for (; j + 3 * kG < b; j += 4 * kG) {
-                int32_t c[4];
-                double2 v[4];
-                double2x2 xx[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) c[q] = ld_stream<1>(colidx + j + q * kG, stream);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = ld_stream<1>(vals + j + q * kG, stream);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) xx[q] = ld256(X + (int64_t)c[q] * K);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    mcfma(acc[0], v[q], xx[q].a);
-                    mcfma(acc[K - 1], v[q], xx[q].b);
-                }
-            }
-            for (; j < b; j += kG) {
-                const int32_t c0 = ld_stream<1>(colidx + j, stream);
-                const double2 v0 = ld_stream<1>(vals + j, stream);
-                const double2x2 xx = ld256(X + (int64_t)c0 * K);
-                mcfma(acc[0], v0, xx.a);
-                mcfma(acc[K - 1], v0, xx.b);
-            }
-        } else {
         for (; j + kG < b; j += 2 * kG) {  // two independent (index, value, gather) streams per lane
             const int32_t c0 = ld_stream<1>(colidx + j, stream), c1 = ld_stream<1>(colidx + j + kG, stream);
             const double2 v0 = ld_stream<1>(vals + j, stream), v1 = ld_stream<1>(vals + j + kG, stream);
             const double2 *x0 = X + (int64_t)c0 * K, *x1 = X + (int64_t)c1 * K;
             double2 xa[K], xb[K];
-            if (K >= 4) {  // 32-byte sectors in one request each
+            if (K >= 2) {  // 32-byte sectors in one request each (see ld256_stream)
 #pragma unroll
                 for (int r = 0; r < K; r += 2) {
                     const double2x2 ta = ld256(x0 + r), tb = ld256(x1 + r);
@@ -103,7 +76,6 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t rows, const int64_t *
             const double2 *x0 = X + (int64_t)c0 * K;
 #pragma unroll
             for (int r = 0; r < K; ++r) mcfma(acc[r], v0, __ldg(x0 + r));
-        }
         }
         // butterfly: every lane ends with the row sums, lane r stores right-hand side r (coalesced)
 #pragma unroll
