@@ -268,6 +268,13 @@ int pg_spmm(int64_t local_rows, const int64_t *rowptr, const int32_t *colidx, co
 /* the same through the plan's 2x2 entity blocks (p = 2, k = 2, 4, 8): see pg_spmv_blocked */
 int pg_spmm_blocked(const pg_plan *plan, const int32_t *colstart, const double *vals, int k, const double *X,
                     const double *dscale, double *Y, void *stream);
+/* pg_spmv_blocked / pg_spmm_blocked (k = 1, 4, 8) fused with the dot product COCG / COCR take right after it:
+ * out[r] = sum_rows X[row,r] Y[row,r] (unconjugated; X[row] = the own entries of the multiplied vector), summed
+ * in a fixed order.  work = pg_spmv_dot_workspace_bytes(plan, k); arrays 32-byte aligned (PG_EINVAL otherwise:
+ * fall back to the separate calls). */
+int64_t pg_spmv_dot_workspace_bytes(const pg_plan *plan, int k);
+int pg_spmm_blocked_dot(const pg_plan *plan, const int32_t *colstart, const double *vals, int k, const double *X,
+                        const double *dscale, double *Y, double *out, void *work, void *stream);
 /* Y[:,r] += alpha[r] X[:,r] */
 int pg_zbaxpy(int64_t n, int k, const double *alpha, const double *X, double *Y, void *stream);
 /* Y[:,r] = X[:,r] + beta[r] Y[:,r] */
@@ -285,6 +292,10 @@ int pg_cocr_update(int64_t n, int k, const double *alpha2, const double *P, cons
                    double *X, double *RT, void *stream);
 int pg_cocr_direction(int64_t n, int k, const double *beta, const double *RT, const double *ART, double *P,
                       double *AP, void *stream);
+/* pg_cocr_direction, and in the same pass out[r] = sum_i AP[i,r] w[i] AP[i,r] of the NEW A p (w = D^-1 or NULL):
+ * the dot product that opens the next COCR iteration, without re-reading A p and D^-1 */
+int pg_cocr_direction_dot(int64_t n, int k, const double *beta, const double *RT, const double *ART, const double *w,
+                          double *P, double *AP, double *out, void *work, void *stream);
 /* out[r] = sum_i |X[i,r]|^2 */
 int pg_zbnrm2sq(int64_t n, int k, const double *X, double *out, void *work, void *stream);
 /* out[r] = a[r] / b[r] (0 where b[r] == 0), out[k + r] = -out[r] */

@@ -179,6 +179,9 @@ SIGNATURES = {
     "pg_tune_spmv_chunk": (C.c_int, [_i32]),
     "pg_phi_gemm_workspace_doubles": (_i64, [_i64, _i32, _i32]),
     "pg_element_matrices_phi_gemm": (C.c_int, [_i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
+    "pg_cocr_direction_dot": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pg_spmv_dot_workspace_bytes": (_i64, [_p, _i32]),
+    "pg_spmm_blocked_dot": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "pg_cocg_step": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -267,6 +267,30 @@ __global__ void __launch_bounds__(256) cocr_direction_kernel(int64_t ntot, const
     }
 }
 
+// the same pass, and the weighted dot product of the NEW A p with itself that opens the next iteration:
+// partial sums of AP[i,r] w[i] AP[i,r] (w = D^-1; fixed reduction grid)
+template <int K>
+__global__ void __launch_bounds__(kRedThreadsM) cocr_direction_dot_kernel(int64_t ntot, const double2 *__restrict__ beta,
+                                                                          const double2 *__restrict__ RT,
+                                                                          const double2 *__restrict__ ART,
+                                                                          const double2 *__restrict__ w,
+                                                                          double2 *__restrict__ P,
+                                                                          double2 *__restrict__ AP,
+                                                                          double2 *__restrict__ partial) {
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double2 be = beta[i0 & (K - 1)];
+    double2 acc[1] = {make_double2(0.0, 0.0)};
+    for (int64_t i = i0; i < ntot; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = RT[i], ap = ART[i];
+        mcfma(p, be, P[i]);
+        mcfma(ap, be, AP[i]);
+        P[i] = p;
+        AP[i] = ap;
+        mcfma(acc[0], ap, w ? mcmul(__ldg(w + i / K), ap) : ap);
+    }
+    block_reduce_store_rhs<K, 1>(acc, partial);
+}
+
 // out[r] = a[r] / b[r] (0 when b[r] == 0: an all-zero right-hand side stays zero), out[K + r] = -out[r]
 __global__ void zbdiv_kernel(int k, const double2 *__restrict__ a, const double2 *__restrict__ b,
                              double2 *__restrict__ out) {
@@ -405,6 +429,20 @@ int pg_cocr_direction(int64_t n, int k, const double *beta, const double *RT, co
 #define CALL(KK) cocr_direction_kernel<KK><<<ew_blocks(n * k), 256, 0, st>>>(n * k, CD2(beta), CD2(RT), CD2(ART), D2(P), D2(AP))
     PG_K_SWITCH(k, CALL)
 #undef CALL
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+int pg_cocr_direction_dot(int64_t n, int k, const double *beta, const double *RT, const double *ART, const double *w,
+                          double *P, double *AP, double *out, void *work, void *stream) {
+    PG_REQUIRE(n >= 0 && valid_k(k), PG_EINVAL, "pg_cocr_direction_dot: bad size");
+    PG_REQUIRE(beta && RT && ART && P && AP && out && work, PG_EINVAL, "pg_cocr_direction_dot: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(KK) cocr_direction_dot_kernel<KK><<<kRedBlocksM, kRedThreadsM, 0, st>>>(n * k, CD2(beta), CD2(RT), CD2(ART), CD2(w), D2(P), D2(AP), D2(work))
+    PG_K_SWITCH(k, CALL)
+#undef CALL
+    PG_LAUNCH_OK();
+    reduce_stage2_m<<<k, kRedThreadsM, 0, st>>>(CD2(work), D2(out));
     PG_LAUNCH_OK();
     return PG_OK;
 }

@@ -8,6 +8,8 @@
 // (solver.py:589, inside KSP).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "pg_plan.cuh"
 
 namespace pg {
@@ -98,16 +100,21 @@ __global__ void __launch_bounds__(256, 6) spmv_blocked2_kernel(int64_t nb, const
 // The same kernel with 256-bit loads: every 2x1 block of values and every (x[c], x[c+1]) pair is ONE request for
 // ONE 32-byte sector (all of them are 32-byte aligned: rows hold an even number of entries, entities start on
 // even dofs, the halo keeps the two dofs of a column entity adjacent).
+// DOT: the block also leaves sum_rows x[row] * y[row] (unconjugated; x[row] = the multiplied vector's own entry)
+// of its rows in dot_partial[blockIdx.x]: the x^T A x of COCG / COCR without a second pass over x and y.
+template <bool DOT>
 __global__ void __launch_bounds__(256, 6) spmv_blocked2_v256_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
                                                                     const int32_t *__restrict__ colstart,
                                                                     const double2 *__restrict__ vals,
                                                                     const double2 *__restrict__ x,
                                                                     const double2 *__restrict__ dscale,
-                                                                    double2 *__restrict__ y, int chunk) {
+                                                                    double2 *__restrict__ y, int chunk,
+                                                                    double2 *__restrict__ dot_partial) {
     const int lane = threadIdx.x % kBG;
     const int gpb = blockDim.x / kBG;  // in-order grid, see spmv_blocked2_kernel
     const unsigned gm = ((1u << kBG) - 1u) << ((threadIdx.x & 31) / kBG * kBG);
     const uint64_t stream = l2_policy_evict_first();
+    double2 pd = make_double2(0.0, 0.0);
     for (int c = 0; c < chunk; ++c) {
         const int64_t i = (blockIdx.x * (int64_t)chunk + c) * gpb + threadIdx.x / kBG;
         if (i >= nb) break;
@@ -159,8 +166,81 @@ __global__ void __launch_bounds__(256, 6) spmv_blocked2_v256_kernel(int64_t nb, 
             }
             y[row] = a0;
             y[row + 1] = a1;
+            if (DOT) {
+                const double2x2 xr = ld256(x + row);
+                cfma2(pd, xr.a, a0);
+                cfma2(pd, xr.b, a1);
+            }
         }
     }
+    if (DOT) {  // fixed order: lanes of a warp, warps of the block
+        __shared__ double2 s_dot[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pd.x += __shfl_xor_sync(0xffffffffu, pd.x, o);
+            pd.y += __shfl_xor_sync(0xffffffffu, pd.y, o);
+        }
+        if ((threadIdx.x & 31) == 0) s_dot[threadIdx.x >> 5] = pd;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double2 t = s_dot[0];
+            for (int w = 1; w < 8; ++w) {
+                t.x += s_dot[w].x;
+                t.y += s_dot[w].y;
+            }
+            dot_partial[blockIdx.x] = t;
+        }
+    }
+}
+
+// Sum of the per-block partials, two fixed-order levels (the C3 matrix has ~500 000 blocks: one block alone would
+// crawl through 8 MB at the latency of a single CTA).  Level a: kDotRed blocks, block g sums the partials
+// b = g*per .. (g+1)*per of right-hand side r = blockIdx.y into mid[r*kDotRed + g]; level b: one block per
+// right-hand side sums the kDotRed values.
+constexpr int kDotRed = kNumSMs * 4;
+
+__device__ __forceinline__ double2 block_sum_256(double2 a) {
+    __shared__ double2 s[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_down_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_down_sync(0xffffffffu, a.y, o);
+    }
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    double2 t = s[0];
+    for (int w = 1; w < 8; ++w) {
+        t.x += s[w].x;
+        t.y += s[w].y;
+    }
+    return t;  // valid in every thread
+}
+
+__global__ void __launch_bounds__(256) dot_stage2a_var(const double2 *__restrict__ partial, int64_t nblocks, int K,
+                                                       double2 *__restrict__ mid) {
+    const int r = blockIdx.y;
+    const int64_t per = (nblocks + kDotRed - 1) / kDotRed;
+    const int64_t b0 = blockIdx.x * per, b1 = min(b0 + per, nblocks);
+    double2 a = make_double2(0.0, 0.0);
+    for (int64_t b = b0 + threadIdx.x; b < b1; b += 256) {
+        const double2 v = partial[b * K + r];
+        a.x += v.x;
+        a.y += v.y;
+    }
+    const double2 t = block_sum_256(a);
+    if (threadIdx.x == 0) mid[(int64_t)r * kDotRed + blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(256) dot_stage2b_var(const double2 *__restrict__ mid, double2 *__restrict__ out) {
+    const int r = blockIdx.x;
+    double2 a = make_double2(0.0, 0.0);
+    for (int g = threadIdx.x; g < kDotRed; g += 256) {
+        const double2 v = mid[(int64_t)r * kDotRed + g];
+        a.x += v.x;
+        a.y += v.y;
+    }
+    const double2 t = block_sum_256(a);
+    if (threadIdx.x == 0) out[r] = t;
 }
 
 // The same for K interleaved right-hand sides (X[i*K + r], see pg_multi.cu): K lanes share a 2x2 block,
@@ -244,13 +324,15 @@ __global__ void __launch_bounds__(256) spmm_blocked2_kernel(int64_t nb, const En
 // plain loop every step pays two dependent memory latencies (index, then X).  Here the 8 lanes of a group load
 // up to 32 indices of the entity at once (coalesced) and every step takes its index from a register by
 // shuffle, so all X gathers and value loads of the entity are independent of any in-flight load.
-template <int K, int HINT>
+template <int K, int HINT, bool DOT = false>
 __global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const EntHdr *__restrict__ hdr,
                                                                const int32_t *__restrict__ colstart,
                                                                const double2 *__restrict__ vals,
                                                                const double2 *__restrict__ X,
                                                                const double2 *__restrict__ dscale,
-                                                               double2 *__restrict__ Y, int chunk) {
+                                                               double2 *__restrict__ Y, int chunk,
+                                                               double2 *__restrict__ dot_partial = nullptr) {
+    double2 pd = make_double2(0.0, 0.0);  // DOT: sum_rows X[row, r] * Y[row, r] of this thread's right-hand side
     constexpr int NS = kBG / K;  // column entities per step of a group
     const int lane = threadIdx.x % kBG;
     const int r = lane % K, sub = lane / K;
@@ -318,6 +400,28 @@ __global__ void __launch_bounds__(256) spmm_blocked2_pf_kernel(int64_t nb, const
             }
             Y[(int64_t)row * K + r] = a0;
             Y[((int64_t)row + 1) * K + r] = a1;
+            if (DOT) {
+                cfma2(pd, __ldg(X + (int64_t)row * K + r), a0);
+                cfma2(pd, __ldg(X + ((int64_t)row + 1) * K + r), a1);
+            }
+        }
+    }
+    if (DOT) {
+        __shared__ double2 s_dot[8][K];
+#pragma unroll
+        for (int o = 16; o >= K; o >>= 1) {  // lanes l, l ^ o serve the same right-hand side l % K
+            pd.x += __shfl_xor_sync(0xffffffffu, pd.x, o);
+            pd.y += __shfl_xor_sync(0xffffffffu, pd.y, o);
+        }
+        if ((threadIdx.x & 31) < K) s_dot[threadIdx.x >> 5][threadIdx.x & 31] = pd;
+        __syncthreads();
+        if (threadIdx.x < K) {
+            double2 t = s_dot[0][threadIdx.x];
+            for (int w = 1; w < 8; ++w) {
+                t.x += s_dot[w][threadIdx.x].x;
+                t.y += s_dot[w][threadIdx.x].y;
+            }
+            dot_partial[(int64_t)blockIdx.x * K + threadIdx.x] = t;
         }
     }
 }
@@ -434,9 +538,54 @@ extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const
         case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
         case 3: spmv_blocked2_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        case 4: spmv_blocked2_v256_kernel<<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 4: spmv_blocked2_v256_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk, nullptr); break;
         default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
     }
+    PG_LAUNCH_OK();
+    return PG_OK;
+}
+
+// MatMult fused with the unconjugated dot product x^T (A x) that COCG / COCR take right after it
+// (rho = r~^T A r~, p^T A p): out[r] = sum_rows X[row, r] * Y[row, r], deterministic two-stage sum.
+// Needs the 256-bit kernels (32-byte aligned arrays); returns PG_EINVAL otherwise so that the caller
+// falls back to pg_spmv_blocked + pg_zbdotu.
+extern "C" int64_t pg_spmv_dot_workspace_bytes(const pg_plan *pl, int k) {
+    if (!pl) return 0;
+    const int64_t nb = pl->b1 - pl->b0;
+    const int64_t tiles = (nb * kBG + 255) / 256;
+    return (tiles + 1 + kDotRed) * (int64_t)std::max(k, 1) * 16;
+}
+
+extern "C" int pg_spmm_blocked_dot(const pg_plan *pl, const int32_t *colstart, const double *vals, int k,
+                                   const double *X, const double *dscale, double *Y, double *out, void *work,
+                                   void *stream) {
+    PG_REQUIRE(pl && vals && X && Y && out && work, PG_EINVAL, "pg_spmm_blocked_dot: null pointer");
+    PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmm_blocked_dot: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
+    PG_REQUIRE(k == 1 || k == 4 || k == 8, PG_EINVAL, "pg_spmm_blocked_dot: k = %d (1, 4 or 8)", k);
+    PG_REQUIRE(!(((uintptr_t)vals | (uintptr_t)X) & 31), PG_EINVAL, "pg_spmm_blocked_dot: arrays must be 32-byte aligned");
+    const int64_t nb = pl->b1 - pl->b0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb == 0) {
+        PG_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)k * 16, st));
+        return PG_OK;
+    }
+    const int chunk = k == 1 ? (g_spmv_chunk > 0 ? g_spmv_chunk : 1) : 4;
+    const int64_t tiles = (nb * kBG + 255) / 256, blocks = (tiles + chunk - 1) / chunk;
+    const int32_t *cs = colstart ? colstart : pl->colstart;
+    const double2 *v2 = reinterpret_cast<const double2 *>(vals), *x2 = reinterpret_cast<const double2 *>(X);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dscale);
+    double2 *y2 = reinterpret_cast<double2 *>(Y), *part = static_cast<double2 *>(work);
+    if (k == 1)
+        spmv_blocked2_v256_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk, part);
+    else if (k == 4)
+        spmm_blocked2_pf_kernel<4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk, part);
+    else
+        spmm_blocked2_pf_kernel<8, 4, true><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk, part);
+    PG_LAUNCH_OK();
+    double2 *mid = part + (tiles + 1) * (int64_t)k;
+    dot_stage2a_var<<<dim3(kDotRed, k), 256, 0, st>>>(part, blocks, k, mid);
+    PG_LAUNCH_OK();
+    dot_stage2b_var<<<k, 256, 0, st>>>(mid, reinterpret_cast<double2 *>(out));
     PG_LAUNCH_OK();
     return PG_OK;
 }

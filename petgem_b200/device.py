@@ -375,6 +375,26 @@ class CSRMatrix:
         )
         return y
 
+    def mult_fused_dot(self, X: torch.Tensor, Y: torch.Tensor, k: int, out: torch.Tensor) -> bool:
+        """Y = A X (k = 1: vectors, else [n, k] blocks) and out[r] = sum_rows X[row, r] Y[row, r] (unconjugated) in
+        ONE pass (pg_spmm_blocked_dot): the x^T A x of COCG / COCR without re-reading x and A x.  Returns False
+        when this matrix has no fused kernel for the shape (no entity blocks, k = 2, unaligned views): the
+        caller then multiplies and takes the dot product separately."""
+        if self.plan is None or k not in (1, 4, 8) or (X.data_ptr() | self.vals.data_ptr()) & 31:
+            return False
+        if not hasattr(self, "_dot_work"):
+            self._dot_work = {}
+        w = self._dot_work.get(k)
+        if w is None:
+            nbytes = lib().pg_spmv_dot_workspace_bytes(self.plan._h, k)
+            w = self._dot_work[k] = torch.empty((nbytes // 16,), dtype=torch.complex128, device=self.vals.device)
+        check(
+            lib().pg_spmm_blocked_dot(self.plan._h, ptr(self.colstart), ptr(self.vals), k, ptr(X), None, ptr(Y), ptr(out),
+                                      ptr(w), stream_ptr()),
+            "pg_spmm_blocked_dot",
+        )
+        return True
+
     def mult_multi(self, X: torch.Tensor, Y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:
         """Y = A X for k interleaved right-hand sides: X is [N, k], Y [rows, k] (C-contiguous), k in
         {1, 2, 4, 8}.  The matrix is streamed once for all k (several sources / MT polarizations)."""

@@ -269,40 +269,54 @@ class Operator:
         if self.grad is not None:
             self.grad.close()
 
-    def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
-        if self.mode == "p2p" and self.xchg is not None:
-            self._peer_product(x, 1, lambda full: self.A_halo.mult(full, y, row_scale))
-        elif self.mode == "p2p":
-            self.ctx.exchange(x, self.send_idx, self.send_splits, self.recv_splits, self.sendbuf, self.xbuf)
-            self.A_halo.mult(self.xbuf, y, row_scale)
-        elif self.mode == "allgather":
-            self.ctx.gather(x, self.send, self.full)
-            self.A_halo.mult(self.full, y, row_scale)
-        else:
-            self.A.mult(x, y, row_scale)
-        self.spmv_calls += 1
+    def matvec(self, x: torch.Tensor, y: torch.Tensor, row_scale: torch.Tensor = None, dot: torch.Tensor = None):
+        """y = A x on the owned rows.  With `dot` (one complex device scalar) the local part of x^T (A x) is left
+        there by the same kernel when the matrix has a fused form; `self.fused_dot` says whether it was."""
+        self._product(x, y, 1, row_scale, dot)
         return y
 
-    def matmat(self, X: torch.Tensor, Y: torch.Tensor, row_scale: torch.Tensor = None) -> torch.Tensor:
-        """Y = A X for k interleaved right-hand sides (X, Y: [n, k]); one pass over the matrix."""
+    def _product(self, x, y, k, row_scale, dot):
+        self.fused_dot = False
+
+        def mult(A, full):
+            if dot is not None and row_scale is None:
+                self.fused_dot = A.mult_fused_dot(full, y, k, dot)
+            if not self.fused_dot:
+                if k == 1 and full.dim() == 1:
+                    A.mult(full, y, row_scale)
+                else:
+                    A.mult_multi(full, y, row_scale)
+
+        if self.mode == "p2p" and self.xchg is not None:
+            self._peer_product(x, k, lambda full: mult(self.A_halo, full))
+        elif self.mode == "p2p":
+            if x.dim() == 1:
+                self.ctx.exchange(x, self.send_idx, self.send_splits, self.recv_splits, self.sendbuf, self.xbuf)
+                mult(self.A_halo, self.xbuf)
+            else:
+                if getattr(self, "_mm", None) is None or self._mm[0] != k:
+                    dev = x.device
+                    self._mm = (k, torch.zeros((int(sum(self.send_splits)), k), dtype=_C128, device=dev),
+                                torch.zeros((self.n + self.halo_entries, k), dtype=_C128, device=dev))
+                _exchange_multi(self.ctx, x, self.send_idx, self.send_splits, self.recv_splits, self._mm[1], self._mm[2])
+                mult(self.A_halo, self._mm[2])
+        elif self.mode == "allgather":
+            if x.dim() != 1:
+                raise NotImplementedError("multi-right-hand-side SpMV needs the neighbour halo (halo='p2p')")
+            self.ctx.gather(x, self.send, self.full)
+            mult(self.A_halo, self.full)
+        else:
+            mult(self.A, x)
+        self.spmv_calls += 1
+
+    def matmat(self, X: torch.Tensor, Y: torch.Tensor, row_scale: torch.Tensor = None, dot: torch.Tensor = None):
+        """Y = A X for k interleaved right-hand sides (X, Y: [n, k]); one pass over the matrix.  `dot` [k]: see
+        matvec."""
         k = int(X.shape[1])
         if k == 1:  # an [n, 1] block is a vector: every halo mode applies
-            self.matvec(X.reshape(-1), Y.reshape(-1), row_scale)
-            return Y
-        if self.mode == "p2p" and self.xchg is not None:
-            self._peer_product(X, k, lambda full: self.A_halo.mult_multi(full, Y, row_scale))
-        elif self.mode == "p2p":
-            if getattr(self, "_mm", None) is None or self._mm[0] != k:
-                dev = X.device
-                self._mm = (k, torch.zeros((int(sum(self.send_splits)), k), dtype=_C128, device=dev),
-                            torch.zeros((self.n + self.halo_entries, k), dtype=_C128, device=dev))
-            _exchange_multi(self.ctx, X, self.send_idx, self.send_splits, self.recv_splits, self._mm[1], self._mm[2])
-            self.A_halo.mult_multi(self._mm[2], Y, row_scale)
-        elif self.mode == "allgather":
-            raise NotImplementedError("multi-right-hand-side SpMV needs the neighbour halo (halo='p2p')")
+            self._product(X.reshape(-1), Y.reshape(-1), 1, row_scale, dot)
         else:
-            self.A.mult_multi(X, Y, row_scale)
-        self.spmv_calls += 1
+            self._product(X, Y, k, row_scale, dot)
         return Y
 
     def precond(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -734,23 +748,42 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
         check(L.pg_zbdotu(n, k, ptr(Z), ptr(AR), ptr(rho[0]), ptr(work), st()), "pg_zbdotu")
         reduce_(rho[0])
 
+    # Fused dot products (pg_spmm_blocked_dot: r~^T A r~ in the MatMult epilogue; pg_cocr_direction_dot: the next
+    # (A p)^T D^-1 (A p) in the direction pass) save two and one vector passes per iteration on paper.  Measured at
+    # C3 on one B200 they LOSE: the block-level partial sum makes every SpMV block wait for its slowest warp
+    # (COCR + Hiptmair 7.95 -> 8.49 ms per iteration, four sources in lockstep 17.3 -> 20.1 ms), the direction
+    # variant is neutral.  Kept as tested options (tests/test_gpu_path.py), off by default.
+    fuse = os.environ.get("PG_FUSED_SPMV_DOT", "0") == "1"
+    fuse_dir = os.environ.get("PG_FUSED_DIRECTION_DOT", "0") == "1"
+    pq_ready = [False]  # Jacobi: (A p)^T D^-1 (A p) of the next iteration comes out of the direction pass
+
     def iterations_cocr(count):
         cur = 0
         for _ in range(count):
             if general:   # MQ = M^-1 (A p), then the same recurrences with the row scaling dropped
                 op.precond(Q, MQ)
                 check(L.pg_zbdotu(n, k, ptr(Q), ptr(MQ), ptr(pq), ptr(work), st()), "pg_zbdotu")
-            else:
+                reduce_(pq)
+            elif not pq_ready[0]:
                 check(L.pg_zbdotu_w(n, k, ptr(Q), ptr(Q), ptr(dinv), ptr(pq), ptr(work), st()), "pg_zbdotu_w")
-            reduce_(pq)
+                reduce_(pq)
             check(L.pg_zbdiv(k, ptr(rho[cur]), ptr(pq), ptr(alpha2), st()), "pg_zbdiv")
             check(L.pg_cocr_update(n, k, ptr(alpha2), ptr(P), ptr(MQ if general else Q), ptr(dinv), ptr(X), ptr(Z),
                                    st()), "pg_cocr_update")
-            op.matmat(Z, AR)
-            check(L.pg_zbdotu(n, k, ptr(Z), ptr(AR), ptr(rho[cur ^ 1]), ptr(work), st()), "pg_zbdotu")
+            # A r~ and r~^T A r~ in one pass over the matrix when the matrix has the fused kernel
+            op.matmat(Z, AR, dot=rho[cur ^ 1] if fuse else None)
+            if not op.fused_dot:
+                check(L.pg_zbdotu(n, k, ptr(Z), ptr(AR), ptr(rho[cur ^ 1]), ptr(work), st()), "pg_zbdotu")
             reduce_(rho[cur ^ 1])
             check(L.pg_zbdiv(k, ptr(rho[cur ^ 1]), ptr(rho[cur]), ptr(beta2), st()), "pg_zbdiv")
-            check(L.pg_cocr_direction(n, k, ptr(beta2), ptr(Z), ptr(AR), ptr(P), ptr(Q), st()), "pg_cocr_direction")
+            if general or not fuse_dir:
+                check(L.pg_cocr_direction(n, k, ptr(beta2), ptr(Z), ptr(AR), ptr(P), ptr(Q), st()),
+                      "pg_cocr_direction")
+            else:
+                check(L.pg_cocr_direction_dot(n, k, ptr(beta2), ptr(Z), ptr(AR), ptr(dinv), ptr(P), ptr(Q), ptr(pq),
+                                              ptr(work), st()), "pg_cocr_direction_dot")
+                reduce_(pq)
+                pq_ready[0] = True
             cur ^= 1
         if cur:
             rho[0].copy_(rho[1])
@@ -761,8 +794,9 @@ def cocg_multi(op: Operator, B: torch.Tensor, rtol=1e-8, maxit=10000, atol=1e-50
     def iterations_cocg(count):
         cur = 0  # count is even, or the last batch: rho[0] is the current rho on entry and on exit
         for _ in range(count):
-            op.matmat(P, Q)
-            check(L.pg_zbdotu(n, k, ptr(P), ptr(Q), ptr(pq), ptr(work), st()), "pg_zbdotu")
+            op.matmat(P, Q, dot=pq if fuse else None)
+            if not op.fused_dot:
+                check(L.pg_zbdotu(n, k, ptr(P), ptr(Q), ptr(pq), ptr(work), st()), "pg_zbdotu")
             reduce_(pq)
             check(L.pg_zbdiv(k, ptr(rho[cur]), ptr(pq), ptr(alpha2), st()), "pg_zbdiv")
             if general:   # x += alpha p, r -= alpha q, z = M^-1 r, rho' = r^T z, |z|^2

@@ -865,3 +865,50 @@ def test_lockstep_multi_source_solve_matches_single(topo, oracle):
                                                                "ksp_rtol": 1e-12, "ksp_max_it": 20000})
     assert len(resg) == 2 and all(r.converged for r in resg)
     assert np.linalg.norm(Xg.cpu().numpy() - Xh[:, :2]) <= 1e-6 * np.linalg.norm(Xh[:, :2])
+
+
+@pytest.mark.parametrize("k", [1, 4, 8])
+def test_fused_dot_kernels_match_the_separate_calls(topo, k):
+    """pg_spmm_blocked_dot (MatMult + x^T A x in one pass) and pg_cocr_direction_dot (COCR direction update + the
+    weighted dot product of the next iteration) against the separate kernels: same vectors bit for bit, dot
+    products to rounding, and bit-reproducible from run to run (fixed summation order)."""
+    from petgem_b200._lib import check, lib, ptr, stream_ptr
+    from petgem_b200.device import AssemblyPlan, CSRMatrix
+
+    L = lib()
+    el = _elems_from_topo(topo)
+    geo, code = el.geometry()
+    plan = AssemblyPlan(el, 2, order="locality")
+    A = CSRMatrix(*plan.csr(), plan.assemble(geo, code, 2 * np.pi * 2.0, 4e-7 * np.pi), plan.N, plan=plan)
+    n, dev = plan.N, el.device
+    g = torch.Generator(device="cpu").manual_seed(7)
+    rnd = lambda *shape: torch.complex(torch.randn(*shape, generator=g, dtype=torch.float64),  # noqa: E731
+                                       torch.randn(*shape, generator=g, dtype=torch.float64)).to(dev)
+    X = rnd(n, k)
+    Y1, Y2 = torch.empty_like(X), torch.empty_like(X)
+    out = torch.zeros((k,), dtype=torch.complex128, device=dev)
+    if k == 1:
+        A.mult(X.reshape(-1), Y1.reshape(-1))
+        assert A.mult_fused_dot(X.reshape(-1), Y2.reshape(-1), 1, out)
+    else:
+        A.mult_multi(X, Y1)
+        assert A.mult_fused_dot(X, Y2, k, out)
+    assert torch.equal(torch.view_as_real(Y1), torch.view_as_real(Y2))
+    ref = (X * Y1).sum(dim=0)
+    assert (out - ref).abs().max().item() <= 1e-12 * (X.abs() * Y1.abs()).sum(dim=0).max().item()
+    out2 = torch.zeros_like(out)
+    A.mult_fused_dot(X.reshape(-1) if k == 1 else X, Y2.reshape(-1) if k == 1 else Y2, k, out2)
+    assert torch.equal(torch.view_as_real(out), torch.view_as_real(out2))
+    # direction + weighted dot
+    RT, ART, P, AP = rnd(n, k), rnd(n, k), rnd(n, k), rnd(n, k)
+    w, beta = rnd(n), rnd(k)
+    P1, AP1 = P.clone(), AP.clone()
+    check(L.pg_cocr_direction(n, k, ptr(beta), ptr(RT), ptr(ART), ptr(P1), ptr(AP1), stream_ptr()), "direction")
+    work = torch.empty((L.pg_reduce_workspace_bytes(2 * k) // 16,), dtype=torch.complex128, device=dev)
+    pq = torch.zeros((k,), dtype=torch.complex128, device=dev)
+    check(L.pg_cocr_direction_dot(n, k, ptr(beta), ptr(RT), ptr(ART), ptr(w), ptr(P), ptr(AP), ptr(pq), ptr(work),
+                                  stream_ptr()), "direction_dot")
+    assert torch.equal(torch.view_as_real(P), torch.view_as_real(P1))
+    assert torch.equal(torch.view_as_real(AP), torch.view_as_real(AP1))
+    ref = (AP1 * w[:, None] * AP1).sum(dim=0)
+    assert (pq - ref).abs().max().item() <= 1e-12 * (AP1.abs() ** 2 * w.abs()[:, None]).sum(dim=0).max().item()
