@@ -398,6 +398,18 @@ int pg_masked_reciprocal(int64_t n, const uint8_t *mask, double *d, void *stream
 #define PG_COMM_MAX_REDUCE 64
 typedef struct pg_comm pg_comm;
 
+/* Halo set-up of a row block [row_begin, row_end) (what MatSetUpMultiply / VecScatterCreate do for PETSc's MPIAIJ):
+ * pg_halo_columns: the sorted set of GLOBAL columns of the block that other ranks own -> ext [<= nnz] i32 (device),
+ *   *n_ext_host entries.  Their owners follow from the row cuts (binary search on the host); every rank sends
+ *   each owner its part of the list (one all-to-all of the caller's transport) and receives, per destination, the
+ *   rows it must push: send_idx = received global rows - row_begin, segments in rank order (pg_comm_push).
+ * pg_halo_remap: colidx (or the plan's column-entity starts, pg_plan_column_starts) -> the [own | halo] numbering:
+ *   owned column c -> c - row_begin, external column -> (row_end - row_begin) + its position in ext.
+ * Synchronous. */
+int pg_halo_columns(int64_t nnz, const int32_t *colidx, int64_t row_begin, int64_t row_end, int32_t *ext,
+                    int64_t *n_ext_host, void *stream);
+int pg_halo_remap(int64_t nnz, int32_t *colidx, int64_t row_begin, int64_t row_end, const int32_t *ext, int64_t n_ext,
+                  void *stream);
 int pg_ipc_alloc(int64_t bytes, void **ptr, void *handle_host);
 int pg_ipc_open(const void *handle_host, void **ptr);
 int pg_ipc_close(void *ptr);

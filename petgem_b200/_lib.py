@@ -159,6 +159,8 @@ SIGNATURES = {
     "pg_graph_end": (C.c_int, [_p, C.POINTER(_p)]),
     "pg_graph_launch": (C.c_int, [_p, _p]),
     "pg_graph_destroy": (None, [_p]),
+    "pg_halo_columns": (C.c_int, [_i64, _p, _i64, _i64, _p, C.POINTER(_i64), _p]),
+    "pg_halo_remap": (C.c_int, [_i64, _p, _i64, _i64, _p, _i64, _p]),
     "pg_ipc_alloc": (C.c_int, [_i64, C.POINTER(_p), _p]),
     "pg_ipc_open": (C.c_int, [_p, C.POINTER(_p)]),
     "pg_ipc_close": (C.c_int, [_p]),

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cub/cub.cuh>
 
 #include "pg_common.cuh"
 
@@ -178,6 +179,33 @@ __global__ void __launch_bounds__(32) ack_kernel(Peers pp, Local *loc, int rank,
     if ((from_mask >> threadIdx.x) & 1u) st_release_sys(&pp.p[threadIdx.x]->ack_flag[chan][rank], seq);
 }
 
+// ---- halo set-up: which columns of the owned block live on other ranks, and the [own | halo] numbering ----
+__global__ void __launch_bounds__(256) flag_outside_kernel(int64_t nnz, const int32_t *__restrict__ col, int32_t lo,
+                                                           int32_t hi, int32_t *__restrict__ key) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = col[i];
+        key[i] = (c < lo || c >= hi) ? c : 0x7fffffff;  // owned columns sort to the end
+    }
+}
+
+__global__ void __launch_bounds__(256) remap_halo_kernel(int64_t nnz, int32_t *__restrict__ col, int32_t lo, int32_t hi,
+                                                         const int32_t *__restrict__ ext, int32_t n_ext) {
+    const int32_t n = hi - lo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = col[i];
+        if (c >= lo && c < hi) {
+            col[i] = c - lo;
+        } else {  // position in the sorted external list (binary search)
+            int32_t a = 0, b = n_ext;
+            while (a < b) {
+                const int32_t m = (a + b) >> 1;
+                if (__ldg(ext + m) < c) a = m + 1; else b = m;
+            }
+            col[i] = n + a;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace pg
 
@@ -226,6 +254,74 @@ int pg_ipc_close(void *ptr) {
 
 int pg_ipc_free(void *ptr) {
     if (ptr) PG_CUDA_OK(cudaFree(ptr));
+    return PG_OK;
+}
+
+/* ---- halo set-up on the device (what PETSc's MatSetUpMultiply / VecScatterCreate do for an MPIAIJ matrix) ---- */
+int pg_halo_columns(int64_t nnz, const int32_t *colidx, int64_t row_begin, int64_t row_end, int32_t *ext,
+                    int64_t *n_ext_host, void *stream) {
+    PG_REQUIRE(nnz >= 0 && n_ext_host && (nnz == 0 || (colidx && ext)) && row_end >= row_begin, PG_EINVAL,
+               "pg_halo_columns: bad argument");
+    PG_REQUIRE(nnz < (int64_t)1 << 31, PG_ERANGE, "pg_halo_columns: more than 2^31 nonzeros in one block");
+    *n_ext_host = 0;
+    if (nnz == 0) return PG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *key = nullptr, *sorted = nullptr, *uniq = nullptr, *count = nullptr;
+    void *tmp = nullptr;
+    size_t b1 = 0, b2 = 0;
+    int rc = PG_OK;
+    auto cleanup = [&]() {
+        cudaFree(key);
+        cudaFree(sorted);
+        cudaFree(uniq);
+        cudaFree(count);
+        cudaFree(tmp);
+    };
+#define PG_TRYC(expr)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (expr);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            set_error("pg_halo_columns: %s -> %s", #expr, cudaGetErrorString(e_));     \
+            cleanup();                                                                 \
+            return e_ == cudaErrorMemoryAllocation ? PG_ENOMEM : PG_ECUDA;             \
+        }                                                                              \
+    } while (0)
+    PG_TRYC(cudaMalloc((void **)&key, (size_t)nnz * 4));
+    PG_TRYC(cudaMalloc((void **)&sorted, (size_t)nnz * 4));
+    PG_TRYC(cudaMalloc((void **)&uniq, (size_t)nnz * 4));
+    PG_TRYC(cudaMalloc((void **)&count, 4));
+    flag_outside_kernel<<<(unsigned)std::min<int64_t>((nnz + 255) / 256, (int64_t)kNumSMs * 16), 256, 0, st>>>(
+        nnz, colidx, (int32_t)row_begin, (int32_t)row_end, key);
+    PG_TRYC(cudaGetLastError());
+    PG_TRYC(cub::DeviceRadixSort::SortKeys(nullptr, b1, key, sorted, (int)nnz, 0, 32, st));
+    PG_TRYC(cub::DeviceSelect::Unique(nullptr, b2, sorted, uniq, count, (int)nnz, st));
+    PG_TRYC(cudaMalloc(&tmp, std::max(b1, b2)));
+    PG_TRYC(cub::DeviceRadixSort::SortKeys(tmp, b1, key, sorted, (int)nnz, 0, 32, st));
+    PG_TRYC(cub::DeviceSelect::Unique(tmp, b2, sorted, uniq, count, (int)nnz, st));
+    int32_t nu = 0, last = 0;
+    PG_TRYC(cudaMemcpyAsync(&nu, count, 4, cudaMemcpyDeviceToHost, st));
+    PG_TRYC(cudaStreamSynchronize(st));
+    if (nu > 0) {
+        PG_TRYC(cudaMemcpyAsync(&last, uniq + nu - 1, 4, cudaMemcpyDeviceToHost, st));
+        PG_TRYC(cudaStreamSynchronize(st));
+        if (last == 0x7fffffff) --nu;  // the marker of the owned columns
+    }
+    if (nu > 0) PG_TRYC(cudaMemcpyAsync(ext, uniq, (size_t)nu * 4, cudaMemcpyDeviceToDevice, st));
+    PG_TRYC(cudaStreamSynchronize(st));
+#undef PG_TRYC
+    *n_ext_host = nu;
+    cleanup();
+    return rc;
+}
+
+int pg_halo_remap(int64_t nnz, int32_t *colidx, int64_t row_begin, int64_t row_end, const int32_t *ext, int64_t n_ext,
+                  void *stream) {
+    PG_REQUIRE(nnz >= 0 && (nnz == 0 || colidx) && (n_ext == 0 || ext) && row_end >= row_begin, PG_EINVAL,
+               "pg_halo_remap: bad argument");
+    if (nnz == 0) return PG_OK;
+    remap_halo_kernel<<<(unsigned)std::min<int64_t>((nnz + 255) / 256, (int64_t)kNumSMs * 16), 256, 0,
+                        (cudaStream_t)stream>>>(nnz, colidx, (int32_t)row_begin, (int32_t)row_end, ext, (int32_t)n_ext);
+    PG_LAUNCH_OK();
     return PG_OK;
 }
 

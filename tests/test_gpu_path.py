@@ -912,3 +912,30 @@ def test_fused_dot_kernels_match_the_separate_calls(topo, k):
     assert torch.equal(torch.view_as_real(AP), torch.view_as_real(AP1))
     ref = (AP1 * w[:, None] * AP1).sum(dim=0)
     assert (pq - ref).abs().max().item() <= 1e-12 * (AP1.abs() ** 2 * w.abs()[:, None]).sum(dim=0).max().item()
+
+
+def test_halo_setup_entry_points_match_the_python_driver(topo):
+    """pg_halo_columns / pg_halo_remap (the C-ABI halo set-up of a row block) against the torch code of
+    krylov.DistContext.build_halo on a middle row block of the p = 2 matrix."""
+    import ctypes as C
+
+    from petgem_b200._lib import check, lib, ptr, stream_ptr
+    from petgem_b200.device import AssemblyPlan
+
+    L = lib()
+    el = _elems_from_topo(topo)
+    full = AssemblyPlan(el, 2, order="locality")
+    lo, hi = full.entity_aligned_row(full.N // 3), full.entity_aligned_row(2 * full.N // 3)
+    plan = AssemblyPlan(el, 2, order=full.order_host, row_range=(lo, hi))
+    _, colidx = plan.csr()
+    c = colidx.to(torch.int64)
+    outside = (c < lo) | (c >= hi)
+    ext_ref = torch.unique(c[outside])
+    local_ref = torch.where(outside, (hi - lo) + torch.searchsorted(ext_ref, c), c - lo).to(torch.int32)
+    ext = torch.empty_like(colidx)
+    n_ext = C.c_int64(0)
+    check(L.pg_halo_columns(colidx.numel(), ptr(colidx), lo, hi, ptr(ext), C.byref(n_ext), stream_ptr()), "pg_halo_columns")
+    assert n_ext.value == ext_ref.numel() and torch.equal(ext[: n_ext.value].to(torch.int64), ext_ref)
+    col2 = colidx.clone()
+    check(L.pg_halo_remap(col2.numel(), ptr(col2), lo, hi, ptr(ext), n_ext.value, stream_ptr()), "pg_halo_remap")
+    assert torch.equal(col2, local_ref)
