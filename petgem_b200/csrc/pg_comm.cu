@@ -54,6 +54,7 @@ struct Peers {
 struct PushArgs {
     double2 *dst[kMaxRanks];
     long long seg[kMaxRanks + 1];
+    int dsts[kMaxRanks];  // the destination ranks that get entries, compacted
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -127,37 +128,36 @@ __global__ void __launch_bounds__(kMaxRedDoubles) allreduce_kernel(Peers pp, Loc
     }
 }
 
-// grid (bx, world): column d of the grid serves destination rank d
-__global__ void __launch_bounds__(256) push_kernel(PushArgs a, Peers pp, Local *loc, int rank, int world, int chan,
+// grid (bx, ndst): column j of the grid serves the j-th destination rank that gets entries (a.dsts[j])
+__global__ void __launch_bounds__(256) push_kernel(PushArgs a, Peers pp, Local *loc, int rank, int ndst, int chan,
                                                    int k, const double2 *__restrict__ x,
                                                    const int32_t *__restrict__ idx, unsigned long long timeout_ns) {
-    const int d = blockIdx.y;
+    const int d = a.dsts[blockIdx.y];
     const long long cnt = a.seg[d + 1] - a.seg[d];
     const unsigned long long seq = *reinterpret_cast<volatile unsigned long long *>(&loc->push_seq[chan]) + 1;
-    if (cnt > 0) {
-        // the reader must be done with the previous push before its halo entries are overwritten
-        if (threadIdx.x == 0) wait_flag(&pp.p[rank]->ack_flag[chan][d], seq - 1, loc, timeout_ns);
-        __syncthreads();
-        const int32_t *id = idx + a.seg[d];
-        double2 *dst = a.dst[d];
-        const long long total = cnt * k;
-        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-             e += (long long)gridDim.x * blockDim.x) {
-            const long long ent = e / k;
-            const int r = (int)(e - ent * k);
-            dst[e] = x[(long long)__ldg(id + ent) * k + r];
-        }
+    // the reader must be done with the previous push before its halo entries are overwritten
+    if (threadIdx.x == 0) wait_flag(&pp.p[rank]->ack_flag[chan][d], seq - 1, loc, timeout_ns);
+    __syncthreads();
+    const int32_t *id = idx + a.seg[d];
+    double2 *dst = a.dst[d];
+    const long long total = cnt * k;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long ent = e / k;
+        const int r = (int)(e - ent * k);
+        dst[e] = x[(long long)__ldg(id + ent) * k + r];
     }
-    __threadfence_system();
+    // bar.sync orders the block's stores before thread 0, whose system-scope fence is cumulative over them
+    // (the grid-sync pattern): one fence per block instead of one per thread
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned nblocks = gridDim.x * gridDim.y;
         if (atomicAdd(&loc->push_done[chan], 1u) == nblocks - 1) {  // last block: every entry is on its way
             loc->push_done[chan] = 0;
             loc->push_seq[chan] = seq;
             __threadfence_system();
-            for (int r = 0; r < world; ++r)
-                if (a.seg[r + 1] > a.seg[r]) st_release_sys(&pp.p[r]->data_flag[chan][rank], seq);
+            for (int j = 0; j < ndst; ++j) st_release_sys(&pp.p[a.dsts[j]]->data_flag[chan][rank], seq);
         }
     }
 }
@@ -372,16 +372,19 @@ int pg_comm_push(pg_comm *c, int chan, int k, const double *x, const int32_t *se
         a.seg[r] = seg_host[std::min(r, c->world)];
     }
     a.seg[kMaxRanks] = seg_host[c->world];
+    int ndst = 0;
+    for (int r = 0; r < kMaxRanks; ++r) a.dsts[r] = 0;
     for (int r = 0; r < c->world; ++r) {
         const long long cnt = seg_host[r + 1] - seg_host[r];
         PG_REQUIRE(cnt >= 0 && (cnt == 0 || (dst_host[r] && send_idx)), PG_EINVAL, "pg_comm_push: segment %d", r);
         most = std::max(most, cnt);
+        if (cnt > 0) a.dsts[ndst++] = r;
     }
     if (most == 0) return PG_OK;  // nothing to send to anybody: no flags either (the readers expect none)
-    const unsigned bx = (unsigned)std::min<long long>((most * k + 255) / 256, 96);
-    push_kernel<<<dim3(bx, c->world), 256, 0, (cudaStream_t)stream>>>(a, c->peers, c->local, c->rank, c->world, chan, k,
-                                                                      reinterpret_cast<const double2 *>(x), send_idx,
-                                                                      c->timeout_ns);
+    const unsigned bx = (unsigned)std::min<long long>((most * k + 1023) / 1024, 64);  // >= 4 entries per thread
+    push_kernel<<<dim3(bx, ndst), 256, 0, (cudaStream_t)stream>>>(a, c->peers, c->local, c->rank, ndst, chan, k,
+                                                                  reinterpret_cast<const double2 *>(x), send_idx,
+                                                                  c->timeout_ns);
     PG_LAUNCH_OK();
     return PG_OK;
 }

@@ -26,6 +26,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=94)
 ap.add_argument("--iters", type=int, default=60)
 ap.add_argument("--pc", default="jacobi,hiptmair")
+ap.add_argument("--out", default="", help="also write the JSON object to this file (rank 0)")
 args = ap.parse_args()
 world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -105,6 +106,12 @@ for pc in args.pc.split(","):
                                    "sum_us": round(sum(v["us_per_iteration"] for v in per_it.values()), 1),
                                    "wall_us_per_iteration_eager": round(wall / args.iters * 1e6, 1)}
 if rank == 0:
-    print(json.dumps(out))
+    if args.out:
+        with open(args.out, "w") as fh:
+            fh.write(json.dumps(out) + "\n")
+    os.write(1, (json.dumps(out) + "\n").encode())
+sys.stderr.write("rank %d done\n" % rank)
+sys.stderr.flush()
 if world > 1:
+    dist.barrier()
     dist.destroy_process_group()
