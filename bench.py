@@ -187,7 +187,7 @@ def run_reference_arm(args):
         return
     p = args.p
     cores = os.cpu_count() or 1
-    tab = build_case(min(args.m, 24), p)  # element sample only needs a mesh with the same element classes
+    tab = build_case(args.m, p)  # the bench's own mesh (C3: m = 94); each step assembles a random sample of its elements
     nsample = args.cpu_sample or {1: 20000, 2: 6000, 3: 1500, 4: 400, 5: 120, 6: 60}[p]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -204,11 +204,16 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC % p, "value": val, "unit": "elements/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic layered-earth CSEM box p=%d (element sample of the same mesh family)" % p,
-                   "p": p},
+        "config": {"workload": "synthetic layered-earth CSEM box, m=%d -> %d tets, p=%d%s; each step assembles a "
+                               "bounded random sample of its elements"
+                               % (args.m, tab["elemsN"].shape[0], p, " (BASELINE configs[2])" if args.m == 94 else ""),
+                   "tets": int(tab["elemsN"].shape[0]), "p": p},
         "cpu_baseline": {"value": val, "unit": "elements/s", "cores": cores, "kind": "port",
-                         "sample": "%d elements per step: oracle element_system in a %d-process pool + "
-                                   "scatter-add of their cliques" % (nsample, cores)},
+                         "sample": "%d elements of the m=%d mesh per step: oracle element_system in a %d-process pool + "
+                                   "scatter-add of their cliques" % (nsample, args.m, cores),
+                         # context: the unmodified reference (pure Python, cannot travel to the GPU box) needs
+                         # 43 ms per element and core at p = 2 (SURVEY probe of computeElementalMatrices), ~4x this port
+                         "reference_python_ms_per_element_p2": 43.0},
         "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
