@@ -48,34 +48,40 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t rows, const int64_t *
         double2 acc[K];
 #pragma unroll
         for (int r = 0; r < K; ++r) acc[r] = make_double2(0.0, 0.0);
-        int64_t j = a + lane;
-        for (; j + kG < b; j += 2 * kG) {  // two independent (index, value, gather) streams per lane
-            const int32_t c0 = ld_stream<1>(colidx + j, stream), c1 = ld_stream<1>(colidx + j + kG, stream);
-            const double2 v0 = ld_stream<1>(vals + j, stream), v1 = ld_stream<1>(vals + j + kG, stream);
-            const double2 *x0 = X + (int64_t)c0 * K, *x1 = X + (int64_t)c1 * K;
-            double2 xa[K], xb[K];
-            if (K >= 2) {  // 32-byte sectors in one request each (see ld256_stream)
+        // The column indices of NPF steps are loaded up front (one latency for all of them), then the steps run two
+        // at a time (index, value, gather streams): the gathers no longer wait for an index load each
+        // (the plain two-stream loop was latency bound: 0.52 of the copy peak at C4, p = 3, k = 2).
+        constexpr int NPF = K <= 2 ? 8 : 4;  // steps whose indices are in flight together
+        for (int64_t j = a + lane; j < b; j += NPF * kG) {
+            int32_t c[NPF];
 #pragma unroll
-                for (int r = 0; r < K; r += 2) {
-                    const double2x2 ta = ld256(x0 + r), tb = ld256(x1 + r);
-                    xa[r] = ta.a, xa[r + 1 < K ? r + 1 : r] = ta.b, xb[r] = tb.a, xb[r + 1 < K ? r + 1 : r] = tb.b;
+            for (int q = 0; q < NPF; ++q) c[q] = j + q * kG < b ? ld_stream<1>(colidx + j + q * kG, stream) : -1;
+#pragma unroll
+            for (int q = 0; q < NPF; q += 2) {
+                if (c[q] < 0) break;
+                const bool two = c[q + 1] >= 0;
+                const int64_t j1 = two ? j + (q + 1) * kG : j + q * kG;  // always a valid position: loads unconditional
+                const double2 v0 = ld_stream<1>(vals + j + q * kG, stream);
+                double2 v1 = ld_stream<1>(vals + j1, stream);
+                if (!two) v1 = make_double2(0.0, 0.0);
+                const double2 *x0 = X + (int64_t)c[q] * K, *x1 = X + (int64_t)(two ? c[q + 1] : c[q]) * K;
+                double2 xa[K], xb[K];
+                if (K >= 2) {  // 32-byte sectors in one request each (see ld256_stream)
+#pragma unroll
+                    for (int r = 0; r < K; r += 2) {
+                        const double2x2 ta = ld256(x0 + r), tb = ld256(x1 + r);
+                        xa[r] = ta.a, xa[r + 1 < K ? r + 1 : r] = ta.b, xb[r] = tb.a, xb[r + 1 < K ? r + 1 : r] = tb.b;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < K; ++r) xa[r] = __ldg(x0 + r), xb[r] = __ldg(x1 + r);
                 }
-            } else {
 #pragma unroll
-                for (int r = 0; r < K; ++r) xa[r] = __ldg(x0 + r), xb[r] = __ldg(x1 + r);
+                for (int r = 0; r < K; ++r) {
+                    mcfma(acc[r], v0, xa[r]);
+                    mcfma(acc[r], v1, xb[r]);
+                }
             }
-#pragma unroll
-            for (int r = 0; r < K; ++r) {
-                mcfma(acc[r], v0, xa[r]);
-                mcfma(acc[r], v1, xb[r]);
-            }
-        }
-        for (; j < b; j += kG) {
-            const int32_t c0 = ld_stream<1>(colidx + j, stream);
-            const double2 v0 = ld_stream<1>(vals + j, stream);
-            const double2 *x0 = X + (int64_t)c0 * K;
-#pragma unroll
-            for (int r = 0; r < K; ++r) mcfma(acc[r], v0, __ldg(x0 + r));
         }
         // butterfly: every lane ends with the row sums, lane r stores right-hand side r (coalesced)
 #pragma unroll
