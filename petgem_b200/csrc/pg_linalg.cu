@@ -48,29 +48,25 @@ __global__ void __launch_bounds__(256, 6) spmv_kernel(int64_t rows, const int64_
     for (int64_t row = grp; row < rows; row += ngrp) {
         const int64_t a = __ldg(rowptr + row), b = __ldg(rowptr + row + 1);
         double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-        // All column indices of (up to) 8 steps are loaded first -- one latency for the lot, and short rows (p = 1:
-        // ~17 entries) need a single pass -- then the steps run four at a time with unconditional loads (clamped
-        // positions, zeroed values): 2 dependent memory latencies per row instead of 2 per step.
-        for (int64_t j = a + lane; j < b; j += 8 * G) {
-            int32_t c[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) c[q] = j + q * G < b ? ld_stream<HINT>(colidx + j + q * G, stream) : -1;
-#pragma unroll
-            for (int q = 0; q < 8; q += 4) {
-                if (c[q] < 0) break;
-                double2 v[4], xv[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const bool ok = c[q + t] >= 0;
-                    v[t] = ld_stream<HINT>(vals + (ok ? j + (q + t) * G : j + q * G), stream);
-                    if (!ok) v[t] = make_double2(0.0, 0.0);
-                    xv[t] = ld_keep<HINT>(x + (ok ? c[q + t] : c[q]), keep);
-                }
-                cfma(acc0, v[0], xv[0]);
-                cfma(acc1, v[1], xv[1]);
-                cfma(acc0, v[2], xv[2]);
-                cfma(acc1, v[3], xv[3]);
-            }
+        // (loading the indices of 8 steps up front, as spmm_kernel does, was measured SLOWER here: C2, p = 1,
+        // COCR + Jacobi 0.418 -> 0.483 s; at 40 registers the unconditional 4-wide steps serialise)
+        int64_t j = a + lane;
+        // 4 independent (index, value, x) streams per lane: the kernel is latency bound otherwise
+        for (; j + 3 * G < b; j += 4 * G) {
+            const int32_t c0 = ld_stream<HINT>(colidx + j, stream), c1 = ld_stream<HINT>(colidx + j + G, stream);
+            const int32_t c2 = ld_stream<HINT>(colidx + j + 2 * G, stream), c3 = ld_stream<HINT>(colidx + j + 3 * G, stream);
+            const double2 v0 = ld_stream<HINT>(vals + j, stream), v1 = ld_stream<HINT>(vals + j + G, stream);
+            const double2 v2 = ld_stream<HINT>(vals + j + 2 * G, stream), v3 = ld_stream<HINT>(vals + j + 3 * G, stream);
+            const double2 x0 = ld_keep<HINT>(x + c0, keep), x1 = ld_keep<HINT>(x + c1, keep);
+            const double2 x2 = ld_keep<HINT>(x + c2, keep), x3 = ld_keep<HINT>(x + c3, keep);
+            cfma(acc0, v0, x0);
+            cfma(acc1, v1, x1);
+            cfma(acc0, v2, x2);
+            cfma(acc1, v3, x3);
+        }
+        for (; j < b; j += G) {
+            const int32_t c0 = ld_stream<HINT>(colidx + j, stream);
+            cfma(acc0, ld_stream<HINT>(vals + j, stream), ld_keep<HINT>(x + c0, keep));
         }
         acc0.x += acc1.x;
         acc0.y += acc1.y;
