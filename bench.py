@@ -857,7 +857,7 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (asm_ms * 1e-3) / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic_c3.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic_c3.json")
     if p == 2 and args.m == 94 and world == 1 and os.path.exists(tpath):
         t = json.load(open(tpath))["assemble_small_kernel<2>"]
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
