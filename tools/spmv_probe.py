@@ -29,6 +29,7 @@ ap.add_argument("--k", type=int, default=4, help="right-hand sides of the SpMM p
 ap.add_argument("--only", default="both", choices=["both", "block", "whole"])
 ap.add_argument("--quick", action="store_true", help="baseline MatMult only (for ncu captures)")
 ap.add_argument("--quick-floor", action="store_true", help="with --quick: the x-free variant")
+ap.add_argument("--quick-k", type=int, default=1, help="with --quick: right-hand sides (1 = MatMult)")
 ap.add_argument("--persist", action="store_true", help="also the access-policy-window runs (measured slower)")
 ap.add_argument("--fetch", action="store_true", help="also the L2 fetch granularity runs (measured neutral)")
 args = ap.parse_args()
@@ -98,6 +99,11 @@ def probe(label, world, rank):
     if args.quick:
         if args.quick_floor:
             A = CSRMatrix(rowptr, colidx, vals, nx, lo, plan=plan, colstart=(cs32 & 0x1FFE).contiguous(), blocked=True)
+        if args.quick_k > 1:
+            Xq = torch.randn((nx, args.quick_k), dtype=torch.complex128, device=dev)
+            Yq = torch.empty((n, args.quick_k), dtype=torch.complex128, device=dev)
+            emit("spmm k=%d" % args.quick_k, timed(lambda: A.mult_multi(Xq, Yq), 2))
+            return
         emit("hints=1" + (" floor" if args.quick_floor else ""), timed(lambda: A.mult(x, y), 2))
         return
     # reference points: a pure read stream over the matrix values, and a copy of them
