@@ -214,6 +214,14 @@ int pg_spmv_scaled(int64_t local_rows, const int64_t *rowptr, const int32_t *col
  *             pg_plan_column_starts() indexing a [own | halo] vector in multi-GPU runs */
 int pg_spmv_blocked(const pg_plan *plan, const int32_t *colstart, const double *vals, const double *x,
                     const double *dscale, double *y, void *stream);
+/* the same for the entities [ent_begin, ent_end) of the plan's processing order only, and the interior range of a
+ * row block whose columns are numbered [own | halo]: every entity of [*ent_begin_host, *ent_end_host) has all its
+ * columns below n_own, so its rows can be multiplied while the halo is still in flight (pg_comm_push), the two
+ * remaining ranges after pg_comm_wait */
+int pg_spmv_blocked_range(const pg_plan *plan, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                          const double *vals, const double *x, const double *dscale, double *y, void *stream);
+int pg_plan_halo_split(const pg_plan *plan, const int32_t *colstart, int64_t n_own, int64_t *ent_begin_host,
+                       int64_t *ent_end_host, void *stream);
 int64_t pg_plan_num_column_entities(const pg_plan *plan);
 int pg_plan_column_starts(const pg_plan *plan, int32_t *colstart, void *stream);
 /* diag [local_rows] complex128 of the owned block (for PCJACOBI) */
@@ -275,6 +283,8 @@ int pg_spmm_blocked(const pg_plan *plan, const int32_t *colstart, const double *
 int64_t pg_spmv_dot_workspace_bytes(const pg_plan *plan, int k);
 int pg_spmm_blocked_dot(const pg_plan *plan, const int32_t *colstart, const double *vals, int k, const double *X,
                         const double *dscale, double *Y, double *out, void *work, void *stream);
+int pg_spmm_blocked_range(const pg_plan *plan, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                          const double *vals, int k, const double *X, const double *dscale, double *Y, void *stream);
 /* Y[:,r] += alpha[r] X[:,r] */
 int pg_zbaxpy(int64_t n, int k, const double *alpha, const double *X, double *Y, void *stream);
 /* Y[:,r] = X[:,r] + beta[r] Y[:,r] */

@@ -115,6 +115,9 @@ SIGNATURES = {
     "pg_spmv": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p]),
     "pg_spmv_scaled": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "pg_spmv_blocked": (C.c_int, [_p, _p, _p, _p, _p, _p, _p]),
+    "pg_spmv_blocked_range": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "pg_spmm_blocked_range": (C.c_int, [_p, _i64, _i64, _p, _p, _i32, _p, _p, _p, _p]),
+    "pg_plan_halo_split": (C.c_int, [_p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64), _p]),
     "pg_plan_num_column_entities": (_i64, [_p]),
     "pg_plan_column_starts": (C.c_int, [_p, _p, _p]),
     "pg_csr_diagonal": (C.c_int, [_i64, _i64, _p, _p, _p, _p, _p]),

@@ -508,6 +508,50 @@ __global__ void __launch_bounds__(256) spmm_blocked2_lane_kernel(int64_t nb, con
 
 using namespace pg;
 
+// entities (processing order) whose column list reaches beyond the owned columns [0, n_own): flagged; the interior
+// range is what lies between the last flagged entity of the first half and the first flagged one of the second half
+__global__ void __launch_bounds__(256) halo_split_kernel(int64_t nb, const pg::EntHdr *__restrict__ hdr,
+                                                         const int32_t *__restrict__ colstart, int32_t n_own,
+                                                         int *__restrict__ lo_hi) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const pg::EntHdr h = hdr[i];
+    const int nc = h.L >> 1;
+    bool out = false;
+    for (int j = 0; j < nc; ++j) out |= colstart[h.cbase + j] >= n_own;
+    if (out) {
+        if (i < nb / 2) atomicMax(lo_hi, (int)i + 1);
+        else atomicMin(lo_hi + 1, (int)i);
+    }
+}
+
+extern "C" int pg_plan_halo_split(const pg_plan *pl, const int32_t *colstart, int64_t n_own, int64_t *ent_begin_host,
+                                  int64_t *ent_end_host, void *stream) {
+    PG_REQUIRE(pl && colstart && ent_begin_host && ent_end_host, PG_EINVAL, "pg_plan_halo_split: null pointer");
+    PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_plan_halo_split: p = 2 only (entity-blocked MatMult)");
+    const int64_t nb = pl->b1 - pl->b0;
+    *ent_begin_host = 0;
+    *ent_end_host = nb;
+    if (nb == 0) return PG_OK;
+    PG_REQUIRE(nb < ((int64_t)1 << 31), PG_ERANGE, "pg_plan_halo_split: too many entities");
+    int *d = nullptr;
+    int h[2] = {0, (int)nb};
+    PG_CUDA_OK(cudaMalloc((void **)&d, 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(d, h, 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        halo_split_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, pl->hdr, colstart, (int32_t)n_own, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    PG_CUDA_OK(e);
+    *ent_begin_host = h[0];
+    *ent_end_host = std::max(h[0], h[1]);
+    return PG_OK;
+}
+
 static int g_spmm_pf = -1;
 static int g_spmv_chunk = 0;
 extern "C" int pg_tune_spmv_chunk(int chunk) {  // consecutive 32-entity tiles per block of pg_spmv_blocked
@@ -519,12 +563,26 @@ extern "C" int pg_tune_spmm_prefetch(int mode) {
     return PG_OK;
 }
 
+extern "C" int pg_spmv_blocked_range(const pg_plan *pl, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                                     const double *vals, const double *x, const double *dscale, double *y, void *stream);
+
 extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const double *vals, const double *x,
                                const double *dscale, double *y, void *stream) {
+    PG_REQUIRE(pl, PG_EINVAL, "pg_spmv_blocked: null pointer");
+    return pg_spmv_blocked_range(pl, 0, pl->b1 - pl->b0, colstart, vals, x, dscale, y, stream);
+}
+
+// the rows of the entities [ent_begin, ent_end) of the plan's processing order only (interior / boundary split of
+// the multi-GPU MatMult: the interior rows need no halo and run while it is in flight)
+extern "C" int pg_spmv_blocked_range(const pg_plan *pl, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                                     const double *vals, const double *x, const double *dscale, double *y, void *stream) {
     PG_REQUIRE(pl && vals && x && y, PG_EINVAL, "pg_spmv_blocked: null pointer");
     PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmv_blocked: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
-    const int64_t nb = pl->b1 - pl->b0;
+    PG_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= pl->b1 - pl->b0, PG_EINVAL,
+               "pg_spmv_blocked_range: entity range [%lld, %lld)", (long long)ent_begin, (long long)ent_end);
+    const int64_t nb = ent_end - ent_begin;
     if (nb == 0) return PG_OK;
+    const EntHdr *hdr0 = pl->hdr + ent_begin;
     const int chunk = g_spmv_chunk > 0 ? g_spmv_chunk : 1;
     const int64_t tiles = (nb * kBG + 255) / 256, blocks = (tiles + chunk - 1) / chunk;
     const int32_t *cs = colstart ? colstart : pl->colstart;
@@ -535,11 +593,11 @@ extern "C" int pg_spmv_blocked(const pg_plan *pl, const int32_t *colstart, const
     int mode = spmv_hint_mode();
     if (mode == 4 && (((uintptr_t)vals | (uintptr_t)x) & 31)) mode = 1;  // 256-bit loads need 32-byte aligned arrays
     switch (mode) {
-        case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        case 3: spmv_blocked2_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
-        case 4: spmv_blocked2_v256_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk, nullptr); break;
-        default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+        case 1: spmv_blocked2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk); break;
+        case 2: spmv_blocked2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk); break;
+        case 3: spmv_blocked2_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk); break;
+        case 4: spmv_blocked2_v256_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk, nullptr); break;
+        default: spmv_blocked2_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
     return PG_OK;
@@ -590,13 +648,27 @@ extern "C" int pg_spmm_blocked_dot(const pg_plan *pl, const int32_t *colstart, c
     return PG_OK;
 }
 
+extern "C" int pg_spmm_blocked_range(const pg_plan *pl, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                                     const double *vals, int k, const double *X, const double *dscale, double *Y,
+                                     void *stream);
+
 extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const double *vals, int k, const double *X,
                                const double *dscale, double *Y, void *stream) {
+    PG_REQUIRE(pl, PG_EINVAL, "pg_spmm_blocked: null pointer");
+    return pg_spmm_blocked_range(pl, 0, pl->b1 - pl->b0, colstart, vals, k, X, dscale, Y, stream);
+}
+
+extern "C" int pg_spmm_blocked_range(const pg_plan *pl, int64_t ent_begin, int64_t ent_end, const int32_t *colstart,
+                                     const double *vals, int k, const double *X, const double *dscale, double *Y,
+                                     void *stream) {
     PG_REQUIRE(pl && vals && X && Y, PG_EINVAL, "pg_spmm_blocked: null pointer");
     PG_REQUIRE(pl->p == 2, PG_EINVAL, "pg_spmm_blocked: only p = 2 has uniform 2x2 entity blocks (p = %d)", pl->p);
     PG_REQUIRE(k == 2 || k == 4 || k == 8, PG_EINVAL, "pg_spmm_blocked: k = %d (2, 4 or 8)", k);
-    const int64_t nb = pl->b1 - pl->b0;
+    PG_REQUIRE(ent_begin >= 0 && ent_begin <= ent_end && ent_end <= pl->b1 - pl->b0, PG_EINVAL,
+               "pg_spmm_blocked_range: entity range [%lld, %lld)", (long long)ent_begin, (long long)ent_end);
+    const int64_t nb = ent_end - ent_begin;
     if (nb == 0) return PG_OK;
+    const EntHdr *hdr0 = pl->hdr + ent_begin;
     static const int chunk_env = [] {
         const char *e = getenv("PG_SPMM_CHUNK");
         return e ? atoi(e) : 0;
@@ -617,18 +689,18 @@ extern "C" int pg_spmm_blocked(const pg_plan *pl, const int32_t *colstart, const
     }();
     const int pf = g_spmm_pf >= 0 ? g_spmm_pf : pf_env;
     switch (k) {
-        case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk); break;
+        case 2: spmm_blocked2_lane_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk); break;
         case 4:
-            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<4, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<4, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else if (pf) spmm_blocked2_pf_kernel<4, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<4, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<4, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else if (pf) spmm_blocked2_pf_kernel<4, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else spmm_blocked2_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
             break;
         default:
-            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<8, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<8, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else if (pf) spmm_blocked2_pf_kernel<8, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
-            else spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, pl->hdr, cs, v2, x2, d2, y2, chunk);
+            if (pf && spmv_hint_mode() == 4 && !((uintptr_t)vals & 31)) spmm_blocked2_pf_kernel<8, 4><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else if (pf && spmv_hint_mode() == 3) spmm_blocked2_pf_kernel<8, 3><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else if (pf) spmm_blocked2_pf_kernel<8, 1><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
+            else spmm_blocked2_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(nb, hdr0, cs, v2, x2, d2, y2, chunk);
     }
     PG_LAUNCH_OK();
     return PG_OK;

@@ -356,18 +356,37 @@ class CSRMatrix:
         self.plan = self.plan_ref if blocked else None
         self.colstart = colstart  # None = the plan's own global column starts
 
-    def mult(self, x: torch.Tensor, y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:
+    def halo_split(self, n_own: int):
+        """(ent_begin, ent_end, n_entities): the entities (plan processing order) in [ent_begin, ent_end) touch no
+        column >= n_own, i.e. no halo entry of an [own | halo] vector; None without entity blocks."""
+        if self.plan is None or self.colstart is None:
+            return None
+        import ctypes as C
+        e0, e1 = C.c_int64(0), C.c_int64(0)
+        check(lib().pg_plan_halo_split(self.plan._h, ptr(self.colstart), int(n_own), C.byref(e0), C.byref(e1),
+                                       stream_ptr()), "pg_plan_halo_split")
+        return int(e0.value), int(e1.value), self.rows // 2  # p = 2: two rows per owned entity
+
+    def mult(self, x: torch.Tensor, y: torch.Tensor = None, row_scale: torch.Tensor = None, ent_range=None) -> torch.Tensor:
         """y = A x  (MatMult); x has N entries, y the owned rows.  With row_scale, y = row_scale .* (A x)
-        (the Jacobi preconditioner applied in the SpMV epilogue)."""
+        (the Jacobi preconditioner applied in the SpMV epilogue).  ent_range = (a, b): only the rows of the
+        entities [a, b) of the plan's processing order (entity-blocked matrices)."""
         if y is None:
             y = torch.empty((self.rows,), dtype=torch.complex128, device=x.device)
         if self.plan is not None:
+            if ent_range is not None:
+                check(lib().pg_spmv_blocked_range(self.plan._h, int(ent_range[0]), int(ent_range[1]), ptr(self.colstart),
+                                                  ptr(self.vals), ptr(x), ptr(row_scale), ptr(y), stream_ptr()),
+                      "pg_spmv_blocked_range")
+                return y
             check(
                 lib().pg_spmv_blocked(self.plan._h, ptr(self.colstart), ptr(self.vals), ptr(x), ptr(row_scale),
                                       ptr(y), stream_ptr()),
                 "pg_spmv_blocked",
             )
             return y
+        if ent_range is not None:
+            raise PetgemB200Error("mult: ent_range needs the entity-blocked form")
         check(
             lib().pg_spmv_scaled(self.rows, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x),
                                  ptr(row_scale), ptr(y), stream_ptr()),
@@ -395,7 +414,7 @@ class CSRMatrix:
         )
         return True
 
-    def mult_multi(self, X: torch.Tensor, Y: torch.Tensor = None, row_scale: torch.Tensor = None) -> torch.Tensor:
+    def mult_multi(self, X: torch.Tensor, Y: torch.Tensor = None, row_scale: torch.Tensor = None, ent_range=None) -> torch.Tensor:
         """Y = A X for k interleaved right-hand sides: X is [N, k], Y [rows, k] (C-contiguous), k in
         {1, 2, 4, 8}.  The matrix is streamed once for all k (several sources / MT polarizations)."""
         k = int(X.shape[1])
@@ -403,6 +422,13 @@ class CSRMatrix:
             Y = torch.empty((self.rows, k), dtype=torch.complex128, device=X.device)
         if not (X.is_contiguous() and Y.is_contiguous()):
             raise PetgemB200Error("mult_multi: X and Y must be C-contiguous [n, k] blocks")
+        if ent_range is not None:
+            if self.plan_ref is None or k not in (2, 4, 8):
+                raise PetgemB200Error("mult_multi: ent_range needs the entity-blocked form and k in (2, 4, 8)")
+            check(lib().pg_spmm_blocked_range(self.plan_ref._h, int(ent_range[0]), int(ent_range[1]), ptr(self.colstart),
+                                              ptr(self.vals), k, ptr(X), ptr(row_scale), ptr(Y), stream_ptr()),
+                  "pg_spmm_blocked_range")
+            return Y
         if self.plan_ref is not None and k in (2, 4, 8):
             # p = 2: the plan's 2x2 entity blocks halve the gathers (measured at C3, k = 4: 10.6 ms against
             # 18.0 ms for the CSR form and 4 x 5.9 ms for four single passes)

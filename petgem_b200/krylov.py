@@ -202,6 +202,7 @@ class Operator:
 
                         self.xchg = PeerExchange(ctx.peer, self.send_idx, self.send_splits, self.recv_splits)
                         self._halo_vectors = {}
+                        self._split = None  # (ent_begin, ent_end, n_entities) of the halo-free rows, set below
                     else:
                         self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
                         self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
@@ -209,6 +210,19 @@ class Operator:
                     cs = ctx.remap_halo(pref.column_starts()) if pref is not None else None
                     self.A_halo = CSRMatrix(A.rowptr, col_l, A.vals, self.n + next_, A.row_begin, plan=pref,
                                             colstart=cs, blocked=A.plan is not None)
+            overlap = os.environ.get("PG_HALO_OVERLAP", "0")  # "1": when at least half the entities are interior; "force"
+            if self.mode == "p2p" and self.xchg is not None and overlap in ("1", "force"):
+                # interior-first MatMult: the entities whose columns are all owned are multiplied while the halo
+                # push is in flight on a second stream; the rest after the flag wait
+                sp = self.A_halo.halo_split(self.n)
+                ok = torch.tensor([1.0 if (sp is not None and sp[1] - sp[0] >= (1 if overlap == "force" else sp[2] // 2))
+                                   else 0.0],
+                                  dtype=torch.float64, device=dev)
+                ctx._sum(ok, ctx.dist.ReduceOp.MIN)  # the same launch sequence on every rank
+                if ok.item() > 0:
+                    self._split = sp
+                    self._comm_stream = torch.cuda.Stream()
+                    self._ev = [torch.cuda.Event(), torch.cuda.Event()]
             if self.mode == "allgather":
                 self.colidx_local = ctx.remap_columns(A.colidx)
                 self.send = torch.zeros((ctx.max_rows,), dtype=_C128, device=dev)
@@ -246,7 +260,7 @@ class Operator:
             self._by_ptr = {v[0].data_ptr(): v for v in self._halo_vectors.values()}
         return hv[0]
 
-    def _peer_product(self, x, k, mult):
+    def _peer_product(self, x, k, mult, ranged=None):
         hv = self._by_ptr.get(x.data_ptr()) if self._halo_vectors else None
         if hv is None or hv[3] != k:
             full = self.halo_vector(None if x.dim() == 1 else k, tag="scratch")  # not resident: one copy of x
@@ -255,6 +269,23 @@ class Operator:
         full = hv[0]
         if full.dim() != x.dim():  # an [n, 1] block and a vector share the layout
             full = full.reshape(-1) if x.dim() == 1 else full.reshape(-1, 1)
+        if self._split is not None and ranged is not None:
+            e0, e1, nb = self._split
+            cur = torch.cuda.current_stream()
+            self._ev[0].record(cur)                      # x is final
+            self._comm_stream.wait_event(self._ev[0])
+            with torch.cuda.stream(self._comm_stream):
+                self.xchg.push(full, k, hv[1])           # overlaps the interior rows
+                self._ev[1].record(self._comm_stream)
+            ranged(full, (e0, e1))
+            cur.wait_event(self._ev[1])
+            self.xchg.wait()
+            if e0 > 0:
+                ranged(full, (0, e0))
+            if e1 < nb:
+                ranged(full, (e1, nb))
+            self.xchg.ack()
+            return
         self.xchg.push(full, k, hv[1])
         self.xchg.wait()
         mult(full)
@@ -288,7 +319,14 @@ class Operator:
                     A.mult_multi(full, y, row_scale)
 
         if self.mode == "p2p" and self.xchg is not None:
-            self._peer_product(x, k, lambda full: mult(self.A_halo, full))
+            ranged = None
+            if self._split is not None and dot is None and (k == 1 or k in (2, 4, 8)):
+                def ranged(full, rng):
+                    if k == 1 and full.dim() == 1:
+                        self.A_halo.mult(full, y, row_scale, ent_range=rng)
+                    else:
+                        self.A_halo.mult_multi(full, y, row_scale, ent_range=rng)
+            self._peer_product(x, k, lambda full: mult(self.A_halo, full), ranged)
         elif self.mode == "p2p":
             if x.dim() == 1:
                 self.ctx.exchange(x, self.send_idx, self.send_splits, self.recv_splits, self.sendbuf, self.xbuf)

@@ -119,8 +119,26 @@ def _worker(rank, world, port, p, out):
         rm = krylov.cocg_multi(op, B2, rtol=1e-10, maxit=4000, method="cocr")
         assert rm.converged.all()
         assert (rm.x[:, 1] - 2j * ref.x[lo:hi]).abs().max().item() <= 2e-7 * ref.x.abs().max().item()
+        # interior-first MatMult: halo push on a second stream while the halo-free rows are multiplied
+        os.environ["PG_HALO_OVERLAP"] = "force"
+        op2 = krylov.Operator(A, pc="jacobi", ctx=ctx, halo="p2p")
+        os.environ["PG_HALO_OVERLAP"] = "0"
+        if p == 2:
+            assert op2._split is not None and 0 <= op2._split[0] <= op2._split[1] <= op2._split[2]
+        y2 = torch.empty_like(y)
+        for _ in range(3):
+            op2.matvec(xg[lo:hi].contiguous(), y2)
+            assert (y2 - yfull[lo:hi]).abs().max().item() <= tol
+        op2.matmat(X4[lo:hi].contiguous(), Y4)
+        assert (Y4[:, 3] - 1j * yfull[lo:hi]).abs().max().item() <= 4 * tol
+        os.environ["PG_CUDA_GRAPH"] = "1"
+        ref_j = krylov.cocr(krylov.Operator(Afull, pc="jacobi"), b, rtol=1e-8, maxit=20000)
+        res_j = krylov.cocr(op2, b[lo:hi].contiguous(), rtol=1e-8, maxit=20000)
+        assert res_j.converged and abs(res_j.iterations - ref_j.iterations) <= 10, (res_j.iterations, ref_j.iterations)
+        assert (res_j.x - ref_j.x[lo:hi]).abs().max().item() <= 1e-6 * ref_j.x.abs().max().item()
         ctx.peer.status()
         torch.cuda.synchronize()
+        op2.close()
         op.close()
         out[rank] = int(res.iterations)
     finally:
