@@ -184,6 +184,10 @@ def main():
     rec = np.frombuffer(raw, dtype="<f8", count=58 * 3, offset=2048).reshape(58, 3)
     assert np.allclose(rec[:, 1], 1750.0) and np.allclose(rec[:, 2], -990.0)
     np.save(os.path.join(GOLD, "case1_receivers.npy"), rec)
+    # the file itself (3.4 KB of DATA written by h5py, no source code) as a fixture of the classic-layout HDF5
+    # reader petgem_b200/h5lite.read_classic (tests/test_host.py)
+    import shutil
+    shutil.copyfile(os.path.join(REF_DATA, "receiver_pos.h5"), os.path.join(GOLD, "receiver_pos_reference.h5"))
 
     # --- reference element loop on the test mesh (solver.py:191-224) -----------------
     sig_table = np.array([1.0, 0.01, 1.0, 3.3333])  # examples/case1 params.yaml:10-11

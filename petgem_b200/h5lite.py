@@ -7,6 +7,11 @@ Specification v3: version-2 superblock, version-2 object headers with their look
 new-style groups, contiguous datasets).  Supported values: python/numpy scalars and arrays of float64, int64,
 complex128 (the compound {r, i} h5py uses), bool (h5py's FALSE/TRUE enum) and strings (fixed-length UTF-8).
 ``read`` parses the same subset back into nested dicts (used by the tests).
+
+``read_classic`` reads the files h5py writes by default -- the format of PETGEM's INPUT files (receiver positions,
+conductivity models: ``preprocessing.py:399-407``, ``tests/data/receiver_pos.h5``): version-0/1 superblock,
+symbol-table groups (B-tree + local heap), version-1 object headers with continuation blocks, contiguous or compact
+datasets of fixed-point / IEEE float / string / {r, i} compound type.  Chunked or filtered datasets are refused.
 """
 from __future__ import annotations
 
@@ -256,3 +261,140 @@ def read(path):
     if eof != len(b):
         raise ValueError("h5lite.read: end-of-file address %d != file size %d" % (eof, len(b)))
     return _read_object(b, root)
+
+
+# ---- reader for the classic layout (what h5py writes by default) -----------------------------------
+def _classic_dtype(b, o):
+    cls, ver = b[o] & 0x0F, b[o] >> 4
+    bits0 = b[o + 1]
+    size = struct.unpack_from("<I", b, o + 4)[0]
+    if cls == 0:
+        return np.dtype(("<" if not bits0 & 1 else ">") + ("i" if bits0 & 0x08 else "u") + str(size))
+    if cls == 1:
+        return np.dtype(("<" if not bits0 & 1 else ">") + "f" + str(size))
+    if cls == 3:
+        return np.dtype("S%d" % size)
+    if cls == 6:  # {r, i} of two equal floats -> complex
+        nmem = b[o + 1] | (b[o + 2] << 8)
+        q = o + 8
+        members = []
+        for _ in range(nmem):
+            e = b.index(b"\0", q)
+            name = b[q:e].decode()
+            if ver < 3:
+                q = q + ((e - q) // 8 + 1) * 8       # name padded to a multiple of 8
+                off = struct.unpack_from("<I", b, q)[0]
+                q += 4 + (28 if ver == 1 else 0)      # v1: dimensionality, permutation, 4 dimension sizes
+            else:
+                nb = 1 if size < 256 else 2 if size < 65536 else 4
+                off = int.from_bytes(b[e + 1:e + 1 + nb], "little")
+                q = e + 1 + nb
+            mt = _classic_dtype(b, q)
+            q += 8 + (12 if mt.kind == "f" else 4)
+            members.append((name, off, mt))
+        if len(members) == 2 and members[0][2] == members[1][2] and members[0][2].kind == "f":
+            return np.dtype("<c%d" % size)
+        return np.dtype({"names": [m[0] for m in members], "formats": [m[2] for m in members],
+                         "offsets": [m[1] for m in members], "itemsize": size})
+    raise ValueError("h5lite.read_classic: datatype class %d is not supported" % cls)
+
+
+def _classic_messages(b, addr):
+    """(type, data offset, size) of every message of a version-1 object header, continuation blocks included."""
+    if b[addr] != 1:
+        raise ValueError("h5lite.read_classic: object header version %d at %d" % (b[addr], addr))
+    nmsg = struct.unpack_from("<H", b, addr + 2)[0]
+    hsize = struct.unpack_from("<I", b, addr + 8)[0]
+    blocks = [(addr + 16, hsize)]
+    out = []
+    while blocks and len(out) < nmsg:
+        o, left = blocks.pop(0)
+        end = o + left
+        while o + 8 <= end and len(out) < nmsg:
+            mtype, msize = struct.unpack_from("<HH", b, o)
+            d = o + 8
+            if mtype == 0x10:  # continuation
+                blocks.append(struct.unpack_from("<QQ", b, d))
+            out.append((mtype, d, msize))
+            o = d + msize
+    return out
+
+
+def _classic_object(b, addr):
+    msgs = _classic_messages(b, addr)
+    kinds = {m[0]: m for m in msgs}
+    if 0x11 in kinds:  # symbol table message: a group
+        btree, heap = struct.unpack_from("<QQ", b, kinds[0x11][1])
+        return _classic_group(b, btree, heap)
+    if 0x01 not in kinds or 0x03 not in kinds or 0x08 not in kinds:
+        raise ValueError("h5lite.read_classic: object at %d is neither a group nor a plain dataset" % addr)
+    d = kinds[0x01][1]
+    ver, rank = b[d], b[d + 1]
+    dims_at = d + (8 if ver == 1 else 4)
+    shape = tuple(struct.unpack_from("<Q", b, dims_at + 8 * i)[0] for i in range(rank))
+    dt = _classic_dtype(b, kinds[0x03][1])
+    L = kinds[0x08][1]
+    if b[L] != 3:
+        raise ValueError("h5lite.read_classic: data layout version %d" % b[L])
+    count = int(np.prod(shape)) if shape else 1
+    if b[L + 1] == 1:
+        a, nbytes = struct.unpack_from("<QQ", b, L + 2)
+        raw = b[a:a + nbytes] if a != _UNDEF else b""
+    elif b[L + 1] == 0:
+        nbytes = struct.unpack_from("<H", b, L + 2)[0]
+        raw = b[L + 4:L + 4 + nbytes]
+    else:
+        raise ValueError("h5lite.read_classic: chunked datasets are not supported (store the array contiguously or "
+                         "convert it to .npy)")
+    if 0x0B in kinds:
+        raise ValueError("h5lite.read_classic: filtered (compressed) datasets are not supported")
+    if len(raw) < count * dt.itemsize:
+        raise ValueError("h5lite.read_classic: dataset shorter than its dataspace")
+    a = np.frombuffer(raw, dtype=dt, count=count).reshape(shape)
+    if dt.kind == "S":
+        vals = [v.rstrip(b"\0").decode() for v in a.reshape(-1)]
+        return vals[0] if shape == () else np.array(vals).reshape(shape)
+    return a[()] if shape == () else a.copy()
+
+
+def _classic_group(b, btree, heap):
+    if b[heap:heap + 4] != b"HEAP":
+        raise ValueError("h5lite.read_classic: no local heap at %d" % heap)
+    names_at = struct.unpack_from("<Q", b, heap + 24)[0]
+    out = {}
+
+    def node(a):
+        if b[a:a + 4] == b"TREE":
+            level, used = b[a + 5], struct.unpack_from("<H", b, a + 6)[0]
+            q = a + 24 + 8  # first child follows key 0
+            for _ in range(used):
+                child = struct.unpack_from("<Q", b, q)[0]
+                node(child)
+                q += 16
+            del level
+        elif b[a:a + 4] == b"SNOD":
+            n = struct.unpack_from("<H", b, a + 6)[0]
+            for i in range(n):
+                e = a + 8 + 40 * i
+                noff, oh = struct.unpack_from("<QQ", b, e)
+                z = b.index(b"\0", names_at + noff)
+                out[b[names_at + noff:z].decode()] = _classic_object(b, oh)
+        else:
+            raise ValueError("h5lite.read_classic: unexpected node at %d" % a)
+
+    node(btree)
+    return out
+
+
+def read_classic(path):
+    """Nested dicts of the groups and datasets of a classic-layout HDF5 file (h5py's default)."""
+    b = open(path, "rb").read()
+    if b[:8] != _SIG:
+        raise ValueError("h5lite.read_classic: %s is not an HDF5 file" % path)
+    if b[8] not in (0, 1):
+        return read(path)  # version-2 superblock: the subset `write` produces
+    if b[13] != 8 or b[14] != 8:
+        raise ValueError("h5lite.read_classic: only 8-byte offsets and lengths")
+    root = 24 + 32 + (4 if b[8] == 1 else 0)  # root symbol table entry
+    oh = struct.unpack_from("<Q", b, root + 8)[0]
+    return _classic_object(b, oh)

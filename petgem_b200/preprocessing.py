@@ -8,6 +8,8 @@ reference), including the MT boundary-element table ``boundaryElements.dat``
 """
 from __future__ import annotations
 
+from struct import error as struct_error
+
 import numpy as np
 
 from . import hvfem
@@ -42,30 +44,38 @@ def read_gmsh22(path):
 
 def read_receivers(path, cols=3, rows=None):
     """Receiver positions [n, 3] (or another [rows, cols] float64 table such as the conductivity model):
-    .npy / text, or the contiguous 'data' dataset of PETGEM's .h5 files.  With h5py the dataset is read
-    properly; without it only the layout h5py gives the shipped single-dataset files is accepted (object
-    headers in the first 2048 bytes, then the float64 rows) and the size is checked against `cols` (and
-    `rows` when known) -- anything else fails loudly instead of being reinterpreted."""
+    .npy / text, or the 'data' dataset of PETGEM's .h5 files (preprocessing.py:399-407).  h5py is used when it is
+    installed; otherwise the file is parsed by h5lite.read_classic (the layout h5py writes by default: symbol-table
+    root group, contiguous dataset).  The shape is checked against `cols` (and `rows` when known): a table of the
+    wrong shape fails loudly instead of being reinterpreted."""
     if path.endswith(".npy"):
-        return np.load(path)
-    if path.endswith(".h5"):
+        data = np.load(path)
+    elif path.endswith(".h5"):
         try:
             import h5py
         except ImportError:
             h5py = None
         if h5py is not None:
             with h5py.File(path, "r") as fh:
-                return fh["data"][()]
-        raw = np.fromfile(path, dtype=np.uint8)
-        body = raw.size - 2048
-        if raw[:8].tobytes() != b"\x89HDF\r\n\x1a\n" or body <= 0 or body % (8 * cols) or \
-                (rows is not None and body != 8 * cols * rows):
-            Print.master("     %s: cannot be read without h5py (expected one contiguous float64 dataset of %s x %d "
-                         "values behind a 2048-byte header); install h5py or convert the file to .npy"
-                         % (path, "n" if rows is None else str(rows), cols))
-            exit(-1)
-        return raw[2048:].view("<f8").reshape(-1, cols)
-    return np.loadtxt(path).reshape(-1, cols)
+                data = fh["data"][()]
+        else:
+            from . import h5lite
+            try:
+                data = h5lite.read_classic(path)["data"]
+            except (ValueError, KeyError, IndexError, struct_error) as err:
+                Print.master("     %s: cannot be read without h5py (%s); install h5py or convert the file to .npy"
+                             % (path, err))
+                exit(-1)
+    else:
+        data = np.loadtxt(path)
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1 and data.size % cols == 0:
+        data = data.reshape(-1, cols)
+    if data.ndim != 2 or data.shape[1] < cols or (rows is not None and data.shape[0] != rows):
+        Print.master("     %s: expected a table of %s x %d values, found shape %s"
+                     % (path, "n" if rows is None else str(rows), cols, data.shape))
+        exit(-1)
+    return data[:, :cols]
 
 
 def locate_points(nodes, elemsN, points, tol=1.0e-12):

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden
+from conftest import GOLDEN, ROOT, golden
 from petgem_b200 import basis, hvfem
 from petgem_b200 import mesh as pmesh
 
@@ -237,3 +237,23 @@ def test_h5lite_roundtrip_and_checksum(tmp_path):
     open(f, "wb").write(bytes(bad))
     with pytest.raises(ValueError):
         h5lite.read(f)
+
+
+def test_h5lite_reads_the_reference_receiver_file(tmp_path):
+    """h5lite.read_classic on tests/golden/receiver_pos_reference.h5 -- the reference's own tests/data/receiver_pos.h5,
+    written by h5py (classic layout: version-0 superblock, symbol-table group, contiguous float64 dataset) -- and
+    preprocessing.read_receivers on top of it (preprocessing.py:399-407) without h5py."""
+    from petgem_b200 import h5lite
+    from petgem_b200.preprocessing import read_receivers
+
+    f = os.path.join(GOLDEN, "receiver_pos_reference.h5")
+    r = h5lite.read_classic(f)
+    rec = golden("case1_receivers.npy")
+    assert set(r) == {"data"} and r["data"].dtype == np.float64 and np.array_equal(r["data"], rec)
+    assert np.array_equal(read_receivers(f), rec)
+    with pytest.raises(SystemExit):  # a [58, 3] table is not a [T, 2] conductivity model
+        read_receivers(f, cols=2, rows=9453)
+    # a file written by h5lite.write is read through the same entry point
+    g = str(tmp_path / "w.h5")
+    h5lite.write(g, {"data": rec})
+    assert np.array_equal(h5lite.read_classic(g)["data"], rec) and np.array_equal(read_receivers(g), rec)
