@@ -6,7 +6,10 @@ the small subset of the HDF5 file format needed for that schema is produced here
 Specification v3: version-2 superblock, version-2 object headers with their lookup3 checksums, compact
 new-style groups, contiguous datasets).  Supported values: python/numpy scalars and arrays of float64, int64,
 complex128 (the compound {r, i} h5py uses), bool (h5py's FALSE/TRUE enum) and strings (fixed-length UTF-8).
-``read`` parses the same subset back into nested dicts (used by the tests).
+``read`` parses the same subset back into nested dicts (used by the tests).  ``write_classic`` produces the same
+tree in the CLASSIC layout instead (version-0 superblock, symbol-table groups, version-1 object headers and
+datatype encodings) -- byte for byte the structures h5py itself writes by default, and what ``Postprocessing``
+uses: ``read_classic`` below, which parses the reference's own h5py-written files, reads it back.
 
 ``read_classic`` reads the files h5py writes by default -- the format of PETGEM's INPUT files (receiver positions,
 conductivity models: ``preprocessing.py:399-407``, ``tests/data/receiver_pos.h5``): version-0/1 superblock,
@@ -296,6 +299,16 @@ def _classic_dtype(b, o):
             return np.dtype("<c%d" % size)
         return np.dtype({"names": [m[0] for m in members], "formats": [m[2] for m in members],
                          "offsets": [m[1] for m in members], "itemsize": size})
+    if cls == 8:  # enumeration: h5py's bool is an int8 enum {FALSE, TRUE}
+        base = _classic_dtype(b, o + 8)
+        nmem = b[o + 1] | (b[o + 2] << 8)
+        q = o + 8 + 8 + (12 if base.kind == "f" else 4)
+        names = []
+        for _ in range(nmem):
+            e = b.index(b"\0", q)
+            names.append(b[q:e])
+            q = q + ((e - q) // 8 + 1) * 8 if ver < 3 else e + 1
+        return np.dtype(bool) if names == [b"FALSE", b"TRUE"] and base.itemsize == 1 else base
     raise ValueError("h5lite.read_classic: datatype class %d is not supported" % cls)
 
 
@@ -398,3 +411,116 @@ def read_classic(path):
     root = 24 + 32 + (4 if b[8] == 1 else 0)  # root symbol table entry
     oh = struct.unpack_from("<Q", b, root + 8)[0]
     return _classic_object(b, oh)
+
+
+# ---- writer of the classic layout ------------------------------------------------------------------
+def _pad8(b):
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _v1_dt_complex128():
+    def member(name, off):
+        return _pad8(name + b"\0") + struct.pack("<IB3xI4x4I", off, 0, 0, 0, 0, 0, 0) + _dt_float64()
+    return struct.pack("<BBBBI", 0x16, 2, 0, 0, 16) + member(b"r", 0) + member(b"i", 8)
+
+
+def _v1_dt_bool():
+    return struct.pack("<BBBBI", 0x18, 2, 0, 0, 1) + _dt_int(1) + _pad8(b"FALSE\0") + _pad8(b"TRUE\0") + b"\x00\x01"
+
+
+def _encode_classic(value):
+    dt, shape, raw = _encode(value)
+    cls = dt[0] & 0x0F
+    if cls == 6:
+        dt = _v1_dt_complex128()
+    elif cls == 8:
+        dt = _v1_dt_bool()
+    return dt, shape, raw
+
+
+def _v1_message(mtype, data, flags=0):
+    data = _pad8(data)
+    return struct.pack("<HHB3x", mtype, len(data), flags) + data
+
+
+def _v1_object_header(messages):
+    body = b"".join(messages)
+    return struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body
+
+
+class _ClassicWriter:
+    INTERNAL_K = 16
+
+    def __init__(self, leaf_k):
+        self.leaf_k = leaf_k
+        self.buf = bytearray(b"\0" * 96)  # superblock + root symbol table entry, filled in at the end
+
+    def _place(self, blob):
+        self.buf.extend(b"\0" * (-len(self.buf) % 8))
+        addr = len(self.buf)
+        self.buf.extend(blob)
+        return addr
+
+    def dataset(self, value):
+        dt, shape, raw = _encode_classic(value)
+        data_addr = self._place(raw) if raw else _UNDEF
+        space = struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+        msgs = [_v1_message(0x01, space), _v1_message(0x03, dt, flags=0x01),
+                _v1_message(0x05, struct.pack("<BBBBI", 2, 2, 2, 1, 0), flags=0x01),
+                _v1_message(0x08, struct.pack("<BBQQ", 3, 1, data_addr, len(raw)))]
+        return self._place(_v1_object_header(msgs))
+
+    def group(self, tree):
+        """-> (object header address, B-tree address, heap address)"""
+        children = []
+        for name, value in tree.items():
+            nm = str(name).encode("utf-8")
+            addr = self.group(value)[0] if isinstance(value, dict) else self.dataset(value)
+            children.append((nm, addr))
+        children.sort(key=lambda c: c[0])  # symbol table entries are ordered by name (strcmp)
+        if len(children) > 2 * self.leaf_k:
+            raise ValueError("h5lite.write_classic: group with more entries than one symbol node holds")
+        # local heap: offset 0 = the empty name (first B-tree key), then the names, null-terminated, 8-byte padded
+        seg = bytearray(b"\0" * 8)
+        offs = []
+        for nm, _ in children:
+            offs.append(len(seg))
+            seg.extend(_pad8(nm + b"\0"))
+        heap_addr = self._place(b"")
+        heap = b"HEAP" + struct.pack("<B3xQQQ", 0, len(seg), 1, heap_addr + 32) + bytes(seg)  # free list: none (1)
+        self.buf.extend(heap)
+        snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(children)))
+        for (nm, addr), off in zip(children, offs):
+            snod.extend(struct.pack("<QQII16x", off, addr, 0, 0))
+        snod.extend(b"\0" * (8 + 2 * self.leaf_k * 40 - len(snod)))
+        snod_addr = self._place(bytes(snod))
+        K = self.INTERNAL_K
+        tree_node = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if children else 0, _UNDEF, _UNDEF))
+        if children:
+            tree_node.extend(struct.pack("<QQQ", 0, snod_addr, offs[-1]))
+        tree_node.extend(b"\0" * (24 + (2 * K + 1) * 8 + 2 * K * 8 - len(tree_node)))
+        btree_addr = self._place(bytes(tree_node))
+        oh = self._place(_v1_object_header([_v1_message(0x11, struct.pack("<QQ", btree_addr, heap_addr))]))
+        return oh, btree_addr, heap_addr
+
+    def finish(self, root):
+        oh, btree, heap = root
+        self.buf.extend(b"\0" * (-len(self.buf) % 8))
+        sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.leaf_k, self.INTERNAL_K, 0)
+        sb += struct.pack("<QQQQ", 0, _UNDEF, len(self.buf), _UNDEF)
+        sb += struct.pack("<QQII", 0, oh, 1, 0) + struct.pack("<QQ", btree, heap)
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        return bytes(self.buf)
+
+
+def _max_entries(tree):
+    return max([len(tree)] + [_max_entries(v) for v in tree.values() if isinstance(v, dict)])
+
+
+def write_classic(path, tree):
+    """The same nested dict as `write`, in the classic layout (what h5py writes by default)."""
+    w = _ClassicWriter(leaf_k=max(4, (_max_entries(tree) + 1) // 2))
+    blob = w.finish(w.group(tree))
+    with open(path, "wb") as fh:
+        fh.write(blob)

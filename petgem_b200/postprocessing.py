@@ -5,7 +5,7 @@ the receiver, E = sum_j x_j N_j, H = sum_j x_j curl N_j / (i omega mu)), vectori
 product's basis tables on the device (pg_locate_points, pg_interpolate_fields).  Output: the reference's
 results file ``<directory>/<mode>_petgemV<version>_<date>.h5`` with its schema (postprocessing.py:341-461:
 groups ``machine`` and ``model``, E/H fields per component, MT impedance / apparent resistivity / phase /
-tipper), written by ``h5lite`` (h5py is not a dependency), plus ``<directory>/fields.npz`` with the same
+tipper), written by ``h5lite.write_classic`` in the layout h5py uses (h5py is not a dependency), plus ``<directory>/fields.npz`` with the same
 arrays; the scratch files are removed afterwards like the reference does (postprocessing.py:463-472) unless
 the parameter file says ``remove_scratch: False``.
 """
@@ -134,8 +134,9 @@ def write_results_h5(inputSetup, out):
     path = (inputSetup.output.get('directory') + '/' + mode + '_petgemV' + CODE_VERSION + '_'
             + str(datetime.today().strftime('%Y-%m-%d')) + '.h5')
     opts = getattr(inputSetup, 'petsc_options', None) or {}
-    h5lite.write(path, results_tree(inputSetup, out, total_num_dofs=out.get('total_num_dofs'),
-                                    solver_type=str(opts.get('ksp_type', 'None'))))
+    # classic layout (version-0 superblock, symbol-table groups): what h5py itself writes by default
+    h5lite.write_classic(path, results_tree(inputSetup, out, total_num_dofs=out.get('total_num_dofs'),
+                                            solver_type=str(opts.get('ksp_type', 'None'))))
     return path
 
 

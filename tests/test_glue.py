@@ -238,7 +238,8 @@ def test_kernel_cli_end_to_end(tmp_path, topo, oracle):
     from petgem_b200 import h5lite
     h5 = glob.glob(str(tmp_path / "out" / "csem_petgemV*.h5"))
     assert len(h5) == 1
-    r = h5lite.read(h5[0])
+    r = h5lite.read_classic(h5[0])
+    assert open(h5[0], "rb").read()[8] == 0  # version-0 superblock: the layout h5py writes
     assert set(r) == {"machine", "model"} and r["machine"]["petgem_version"] == "1.0"
     m = r["model"]
     assert m["mode"] == "csem" and m["nord"] == 1 and m["dof"] == N and bool(m["cuda"])

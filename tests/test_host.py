@@ -231,6 +231,19 @@ def test_h5lite_roundtrip_and_checksum(tmp_path):
     assert np.array_equal(m["E-fields_mode_x"]["x"], tree["model"]["E-fields_mode_x"]["x"])
     assert m["E-fields_mode_x"]["x"].dtype == np.complex128
     assert [m["wide"]["k%02d" % i] for i in range(24)] == list(range(24))
+    # the same tree in the classic layout (what Postprocessing writes; the reader is the one that parses the
+    # reference's h5py-written files)
+    g = str(tmp_path / "c.h5")
+    h5lite.write_classic(g, tree)
+    rawc = open(g, "rb").read()
+    assert rawc[:8] == raw[:8] and rawc[8] == 0 and len(rawc) == int.from_bytes(rawc[40:48], "little")
+    c = h5lite.read_classic(g)
+    assert c["machine"] == tree["machine"]
+    mc = c["model"]
+    assert mc["cuda"] and not mc["vtk"] and mc["nord"] == 2 and mc["run-time (s)"] == 1.25 and mc["polarization"] == "xy"
+    assert np.array_equal(mc["E-fields_mode_x"]["x"], tree["model"]["E-fields_mode_x"]["x"])
+    assert mc["E-fields_mode_x"]["y"].dtype == np.complex128 and mc["apparent_resistivity"]["xx"].dtype == np.float64
+    assert [mc["wide"]["k%02d" % i] for i in range(24)] == list(range(24))
     # a flipped byte in an object header is caught by its checksum
     bad = bytearray(raw)
     bad[raw.index(b"OHDR") + 12] ^= 0x40
