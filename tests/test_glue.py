@@ -345,3 +345,18 @@ def test_kernel_cli_mt_two_polarizations(tmp_path, topo, nord):
         r = b - A.mult(torch.as_tensor(x, device=A.vals.device))
         assert float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(b)) <= 1e-7
     assert os.path.exists(str(tmp_path / "out" / "fields.npz"))
+    # the MT results file (postprocessing.py:424-458): fields per polarization, impedance, apparent resistivity,
+    # phase and tipper
+    import glob
+
+    from petgem_b200 import h5lite
+    h5 = glob.glob(str(tmp_path / "out" / "mt_petgemV*.h5"))
+    assert len(h5) == 1
+    m = h5lite.read_classic(h5[0])["model"]
+    F = np.load(str(tmp_path / "out" / "fields.npz"))
+    assert m["mode"] == "mt" and m["num-polarizations"] == 2 and m["nord"] == nord
+    assert set(m["impedance"]) == {"xx", "xy", "yx", "yy"} and set(m["tipper"]) == {"x", "y"}
+    pol = [k for k in m if k.startswith("E-fields_mode_")]
+    assert len(pol) == 2
+    assert np.array_equal(m["impedance"]["xy"], F["impedance"][1])
+    assert np.array_equal(m["apparent_resistivity"]["yx"], F["apparent_resistivity"][2])
