@@ -270,3 +270,39 @@ def test_h5lite_reads_the_reference_receiver_file(tmp_path):
     g = str(tmp_path / "w.h5")
     h5lite.write(g, {"data": rec})
     assert np.array_equal(h5lite.read_classic(g)["data"], rec) and np.array_equal(read_receivers(g), rec)
+
+
+def test_peer_exchange_offsets_without_a_gpu():
+    """PeerExchange (peer.py): where each rank's segment starts inside the receive area of its destinations, the
+    segment table and the reader mask, from the send/recv counts alone (no CUDA: a stand-in communicator)."""
+    torch = pytest.importorskip("torch")
+    from petgem_b200.peer import PeerExchange
+
+    # recv[d][s] = entries rank d receives from rank s (3 ranks); send[s][d] = recv[d][s]
+    recv = [[0, 4, 2], [3, 0, 0], [5, 1, 0]]
+
+    class Comm:
+        def __init__(self, rank):
+            self.rank, self.world, self._c = rank, 3, 0
+
+        def channel(self):
+            self._c += 1
+            return self._c - 1
+
+        def all_gather_object(self, obj):
+            return recv
+
+    for s in range(3):
+        send_splits = [recv[d][s] for d in range(3)]
+        ex = PeerExchange(Comm(s), torch.arange(sum(send_splits)), send_splits, recv[s])
+        assert list(ex.seg) == [0] + list(np.cumsum(send_splits))
+        assert ex.from_mask == sum(1 << r for r in range(3) if recv[s][r] > 0) and ex.n_recv == sum(recv[s])
+        # my segment in rank d's receive area starts after the segments of the lower ranks
+        assert ex.dst_entry == [sum(recv[d][:s]) for d in range(3)]
+
+        class Buf:
+            addr = [1000, 2000, 3000]
+        table = ex.target(Buf, [64, 128, 256], k=2)
+        for d in range(3):
+            want = (Buf.addr[d] + [64, 128, 256][d] + ex.dst_entry[d] * 2 * 16) if send_splits[d] else None
+            assert table[d] == want
