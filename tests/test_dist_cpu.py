@@ -63,6 +63,11 @@ def _worker(rank, world, port, N, cuts, seed, out):
             _exchange_multi(ctx, torch.from_numpy(Xk[lo:hi].copy()), send_idx, send_splits, recv_splits, sb, xb)
             assert np.array_equal(xb.numpy()[col_h.numpy()], Xk[Aloc.indices])
             assert np.abs(Ap @ xb.numpy() - (A @ Xk)[lo:hi]).max() < 1e-12
+        # decisions taken from per-rank clocks are agreed on (max over ranks), and the set-up helpers reduce
+        assert ctx.transport == "nccl" and ctx.peer is None  # no CUDA here: torch.distributed collectives
+        assert ctx.agree(rank == 1) is True and ctx.agree(False) is False
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        assert ctx._sum(t).item() == 3.0
         # all-reduced dot product equals the global one
         d = torch.tensor([np.vdot(x[lo:hi], y)], dtype=torch.complex128)
         ctx.allreduce(d)

@@ -306,3 +306,45 @@ def test_peer_exchange_offsets_without_a_gpu():
         for d in range(3):
             want = (Buf.addr[d] + [64, 128, 256][d] + ex.dst_entry[d] * 2 * 16) if send_splits[d] else None
             assert table[d] == want
+
+
+def test_results_tree_has_the_reference_schema():
+    """postprocessing.results_tree: the groups / datasets of the reference's results file
+    (postprocessing.py:346-458) for a CSEM and an MT run, from stand-in input objects (no GPU)."""
+    from petgem_b200 import postprocessing as post
+
+    class Setup:
+        pass
+
+    rec = 7
+    f = (np.arange(rec * 6).reshape(rec, 6) * (1 + 0.5j)).astype(np.complex128)
+    s = Setup()
+    s.model = {"mode": "csem", "mesh": "m.msh", "receivers": "r.h5",
+               "csem": {"sigma": {"horizontal": [1.0, 0.01], "vertical": [1.0, 0.01]},
+                        "source": {"frequency": 2.0, "position": [1750.0, 1750.0, -975.0], "azimuth": 0.0, "dip": 0.0,
+                                   "current": 1.0, "length": 1.0}}}
+    s.run = {"nord": 2, "cuda": True, "num_polarizations": 1, "conductivity_from_file": False}
+    s.output = {"vtk": False}
+    t = post.results_tree(s, {"fields_0": f, "run_time_s": 1.5}, total_num_dofs=65574, solver_type="cr")
+    assert set(t) == {"machine", "model"} and set(t["machine"]) == {"machine", "num_processors", "petgem_version"}
+    m = t["model"]
+    for key in ("date", "mesh_file", "receivers_file", "nord", "dof", "cuda", "vtk", "mode", "num-polarizations", "solver",
+                "run-time (s)", "sigma_horizontal (S/m)", "sigma_vertical (S/m)", "frequency (Hz)", "source_position (m)",
+                "source_azimuth (deg)", "source_dip (deg)", "source_current (Am)", "source_length (m)", "E-fields",
+                "H-fields"):
+        assert key in m, key
+    assert m["dof"] == 65574 and m["solver"] == "cr" and np.array_equal(m["E-fields"]["y"], f[:, 1])
+    assert np.array_equal(m["H-fields"]["z"], f[:, 5])
+    # MT: fields per polarization + impedance, apparent resistivity, phase, tipper
+    s.model = {"mode": "mt", "mesh": "m.msh", "receivers": "r.h5",
+               "mt": {"sigma": {"horizontal": [1e-10, 0.01], "vertical": [1e-10, 0.01]}, "frequency": 2.0,
+                      "polarization": "xy"}}
+    s.run["num_polarizations"] = 2
+    four = np.arange(4 * rec).reshape(4, rec).astype(np.complex128)
+    out = {"fields_0": f, "fields_1": 2 * f, "impedance": four, "apparent_resistivity": four.real, "phase": four.real,
+           "tipper": four[:2], "run_time_s": 2.0}
+    m = post.results_tree(s, out, total_num_dofs=10)["model"]
+    assert {"E-fields_mode_x", "H-fields_mode_x", "E-fields_mode_y", "H-fields_mode_y", "impedance",
+            "apparent_resistivity", "phase", "tipper", "polarization", "frequency (Hz)"} <= set(m)
+    assert set(m["impedance"]) == {"xx", "xy", "yx", "yy"} and np.array_equal(m["impedance"]["yx"], four[2])
+    assert np.array_equal(m["E-fields_mode_y"]["x"], 2 * f[:, 0]) and set(m["tipper"]) == {"x", "y"}
