@@ -203,6 +203,9 @@ class Operator:
                         self.xchg = PeerExchange(ctx.peer, self.send_idx, self.send_splits, self.recv_splits)
                         self._halo_vectors = {}
                         self._split = None  # (ent_begin, ent_end, n_entities) of the halo-free rows, set below
+                        # the vector for operands that do not live in peer-mapped memory (GMRES basis vectors, b):
+                        # mapped now, so that the one-off IPC set-up is not paid inside the first solve
+                        self.halo_vector(None, tag="scratch")
                     else:
                         self.sendbuf = torch.zeros((int(sum(self.send_splits)),), dtype=_C128, device=dev)
                         self.xbuf = torch.zeros((self.n + next_,), dtype=_C128, device=dev)
